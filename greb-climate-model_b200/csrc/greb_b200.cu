@@ -1,0 +1,587 @@
+// greb_b200.cu — CUDA runtime + C ABI of the B200-native GREB stepping core (include/greb_b200.h).
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false (exact mode: the
+// reference is compiled without FMA contraction, see greb_core.h).
+//
+// There is NO CPU path in this file: every compute entry point needs an sm_100 device and fails
+// with GREB_E_NO_DEVICE otherwise.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/greb_b200.h"
+#include "greb_core.h"
+#include "greb_setup.h"
+
+// ------------------------------------------------------------------------------------------------
+//                                            kernels
+// ------------------------------------------------------------------------------------------------
+
+#define GREB_SMEM_BYTES (4 * GNC * (int)sizeof(float))
+
+__device__ __forceinline__ void load_member_const(GrebMemberConst* dst, const GrebMemberConst* src) {
+  const int* s = reinterpret_cast<const int*>(src);
+  int* d = reinterpret_cast<int*>(dst);
+  for (int i = threadIdx.x; i < (int)(sizeof(GrebMemberConst) / sizeof(int)); i += blockDim.x) d[i] = s[i];
+  __syncthreads();
+}
+
+// One CTA integrates one ensemble member for a.nsteps 12-hour steps (time_loop, f:239-274, or
+// qflux_correction, f:325-362, selected by a.spinup).
+__global__ void __launch_bounds__(GREB_NTHREADS, 1) greb_member_kernel(const GrebKernelArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  __shared__ GrebMemberConst mc_s;
+  const int member = a.member_ids[blockIdx.x];
+  load_member_const(&mc_s, a.mc + member);
+  SimtCtx ctx;
+  ctx.warp = warp_uniform(threadIdx.x >> 5);
+  ctx.lane_u = threadIdx.x & 31;
+  ctx.smem = smem;
+  member_run(ctx, a, mc_s, member);
+}
+
+// circulation(X_in, dX_crcl, h_scl, wz) (f:528-553): one CTA per field
+__global__ void __launch_bounds__(GREB_NTHREADS, 1) greb_circulation_kernel(const GrebCirculationArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  __shared__ GrebMemberConst mc_s;
+  load_member_const(&mc_s, a.mc);
+  SimtCtx ctx;
+  ctx.warp = warp_uniform(threadIdx.x >> 5);
+  ctx.lane_u = threadIdx.x & 31;
+  ctx.smem = smem;
+  const size_t off = (size_t)blockIdx.x * GNC;
+  const WarpGeom g = warp_geom(ctx, mc_s);
+  CircTile t;
+  circ_load_uv(t, g, a.uv, a.uv + GNC);
+  circ_load_wz(t, g, a.wz + off);
+  circ_load_field(t, g, a.X_in + off);
+  circulation_run(ctx, t, g, mc_s, smem);
+#pragma unroll
+  for (int r = 0; r < GREB_MAXR; ++r)
+    if (r < g.nr) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const int idx = (g.k0 + r) * GX + g.col + c;
+        a.dX[off + idx] = t.Y[r + 2][c] - a.X_in[off + idx];  // f:551
+      }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+//                                            runtime
+// ------------------------------------------------------------------------------------------------
+
+struct greb_b200_handle_s {
+  int device = 0;
+  int n_members = 0;
+  std::string err;
+  bool have_forcing = false, inited = false;
+  GrebHostForcing F;
+  std::vector<greb_physics_par> phys;
+  std::vector<char> have_member;
+  std::vector<std::vector<float>> co2;
+  std::vector<int> year0;
+  std::vector<int> group_of;   // member -> group
+  std::vector<int> group_rep;  // group -> representative member
+  int co2_stride = 0;
+  // device
+  float *d_forc = nullptr, *d_sw = nullptr, *d_zoc = nullptr, *d_toclim = nullptr, *d_tclim = nullptr,
+        *d_qclim = nullptr, *d_wz = nullptr, *d_corr = nullptr, *d_state = nullptr, *d_acc = nullptr,
+        *d_co2 = nullptr, *d_diag = nullptr, *d_coslat = nullptr;
+  float* d_out[2] = {nullptr, nullptr};
+  int *d_mask = nullptr, *d_flags = nullptr, *d_ids_all = nullptr, *d_ids_rep = nullptr;
+  GrebMemberConst* d_mc = nullptr;
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_k[2] = {nullptr, nullptr}, ev_c[2] = {nullptr, nullptr};
+  int it_next = 1;   // step counter `it` of the next scenario step
+  int last_out = 0;  // d_out buffer holding the last completed year
+  float last_ms = 0.f;
+  int last_launches = 0;
+};
+
+static std::string g_create_err;
+
+#define CK(call)                                                                                  \
+  do {                                                                                            \
+    cudaError_t e_ = (call);                                                                      \
+    if (e_ != cudaSuccess) {                                                                      \
+      h->err = std::string(#call) + ": " + cudaGetErrorString(e_);                                \
+      return GREB_E_CUDA;                                                                         \
+    }                                                                                             \
+  } while (0)
+
+static int fail(greb_b200_t h, int code, const std::string& msg) {
+  h->err = msg;
+  return code;
+}
+
+extern "C" const char* greb_b200_last_error(greb_b200_t h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+extern "C" int greb_b200_n_members(greb_b200_t h) { return h ? h->n_members : GREB_E_INVALID; }
+
+extern "C" int greb_b200_create(greb_b200_t* out, int n_members, int device) {
+  if (!out || n_members < 1) {
+    g_create_err = "greb_b200_create: bad arguments";
+    return GREB_E_INVALID;
+  }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) {
+    g_create_err = std::string("greb_b200_create: no usable CUDA device (") +
+                   (e != cudaSuccess ? cudaGetErrorString(e) : "device index out of range") +
+                   "); this library has no CPU fallback";
+    return GREB_E_NO_DEVICE;
+  }
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  if (prop.major != 10) {
+    g_create_err = std::string("greb_b200_create: device '") + prop.name +
+                   "' is not sm_100 (the kernels are built for sm_100a only)";
+    return GREB_E_NO_DEVICE;
+  }
+  greb_b200_t h = new greb_b200_handle_s;
+  h->device = device;
+  h->n_members = n_members;
+  h->phys.resize(n_members);
+  h->have_member.assign(n_members, 0);
+  h->co2.resize(n_members);
+  h->year0.assign(n_members, 1940);
+  for (auto& p : h->phys) greb_b200_physics_defaults(&p);
+  cudaSetDevice(device);
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    g_create_err = "greb_b200_create: cudaStreamCreate failed";
+    delete h;
+    return GREB_E_CUDA;
+  }
+  cudaEventCreate(&h->ev0);
+  cudaEventCreate(&h->ev1);
+  for (int i = 0; i < 2; ++i) {
+    cudaEventCreateWithFlags(&h->ev_k[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_c[i], cudaEventDisableTiming);
+  }
+  cudaFuncSetAttribute(greb_member_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GREB_SMEM_BYTES);
+  cudaFuncSetAttribute(greb_circulation_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GREB_SMEM_BYTES);
+  *out = h;
+  return GREB_OK;
+}
+
+static void free_device(greb_b200_t h) {
+  float** fp[] = {&h->d_forc, &h->d_sw,  &h->d_zoc,   &h->d_toclim, &h->d_tclim,  &h->d_qclim,  &h->d_wz,
+                  &h->d_corr, &h->d_state, &h->d_acc, &h->d_co2,    &h->d_diag,   &h->d_coslat, &h->d_out[0],
+                  &h->d_out[1]};
+  for (float** p : fp) {
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+  }
+  int** ip[] = {&h->d_mask, &h->d_flags, &h->d_ids_all, &h->d_ids_rep};
+  for (int** p : ip) {
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+  }
+  if (h->d_mc) cudaFree(h->d_mc);
+  h->d_mc = nullptr;
+}
+
+extern "C" int greb_b200_destroy(greb_b200_t h) {
+  if (!h) return GREB_E_INVALID;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  free_device(h);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  for (int i = 0; i < 2; ++i) {
+    if (h->ev_k[i]) cudaEventDestroy(h->ev_k[i]);
+    if (h->ev_c[i]) cudaEventDestroy(h->ev_c[i]);
+  }
+  delete h;
+  return GREB_OK;
+}
+
+extern "C" int greb_b200_set_forcing(greb_b200_t h, const float* z_topo, const float* glacier, const float* sw_solar,
+                                     const float* tclim, const float* qclim, const float* swetclim,
+                                     const float* uclim, const float* vclim, const float* mldclim,
+                                     const float* cldclim) {
+  if (!h || !z_topo || !glacier || !sw_solar || !tclim || !qclim || !swetclim || !uclim || !vclim || !mldclim ||
+      !cldclim)
+    return h ? fail(h, GREB_E_INVALID, "greb_b200_set_forcing: null pointer") : GREB_E_INVALID;
+  greb_build_forcing(h->F, z_topo, glacier, sw_solar, tclim, qclim, swetclim, uclim, vclim, mldclim, cldclim);
+  h->have_forcing = true;
+  h->inited = false;
+  return GREB_OK;
+}
+
+extern "C" int greb_b200_set_member(greb_b200_t h, int member, const greb_physics_par* p, const float* co2_ppm,
+                                    int n_years, int year0) {
+  if (!h) return GREB_E_INVALID;
+  if (member < 0 || member >= h->n_members || !p || n_years < 0 || (n_years > 0 && !co2_ppm))
+    return fail(h, GREB_E_INVALID, "greb_b200_set_member: bad arguments");
+  h->phys[member] = *p;
+  h->co2[member].assign(co2_ppm, co2_ppm + n_years);
+  h->year0[member] = year0;
+  h->have_member[member] = 1;
+  h->inited = false;
+  return GREB_OK;
+}
+
+template <class T>
+static cudaError_t upload(T** dptr, const std::vector<T>& v) {
+  cudaError_t e = cudaMalloc((void**)dptr, v.size() * sizeof(T));
+  if (e != cudaSuccess) return e;
+  return cudaMemcpy(*dptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+}
+
+extern "C" int greb_b200_init(greb_b200_t h) {
+  if (!h) return GREB_E_INVALID;
+  if (!h->have_forcing) return fail(h, GREB_E_INVALID, "greb_b200_init: set_forcing has not been called");
+  cudaSetDevice(h->device);
+  free_device(h);
+  const int N = h->n_members;
+  // physics groups: members with identical physics_par share wz fields, spin-up and corrections
+  h->group_of.assign(N, -1);
+  h->group_rep.clear();
+  for (int m = 0; m < N; ++m) {
+    int g = -1;
+    // compare against group representatives (linear scan with a cheap hash of the bytes)
+    for (int gi = (int)h->group_rep.size() - 1; gi >= 0; --gi)
+      if (greb_physics_equal(h->phys[m], h->phys[h->group_rep[gi]])) {
+        g = gi;
+        break;
+      }
+    if (g < 0) {
+      g = (int)h->group_rep.size();
+      h->group_rep.push_back(m);
+    }
+    h->group_of[m] = g;
+  }
+  const int G = (int)h->group_rep.size();
+  // memory check before allocating the big per-group correction arrays
+  size_t need = (size_t)G * GNT * GC_COUNT * GNC * 4 + (size_t)N * (GS_COUNT + GA_COUNT + 2 * 12 * 5) * GNC * 4 +
+                (size_t)GNT * (GF_COUNT + 2) * GNC * 4 + (size_t)G * 2 * GNC * 4;
+  size_t freeb = 0, totalb = 0;
+  cudaMemGetInfo(&freeb, &totalb);
+  if (need + (512u << 20) > freeb) {
+    char buf[256];
+    snprintf(buf, sizeof buf,
+             "greb_b200_init: %d members in %d physics groups need %.1f GB of device memory, %.1f GB free; "
+             "run the ensemble in smaller batches",
+             N, G, need / 1e9, freeb / 1e9);
+    return fail(h, GREB_E_NOMEM, buf);
+  }
+  std::vector<GrebMemberConst> mc(N);
+  std::vector<float> state((size_t)N * GS_COUNT * GNC), wz((size_t)G * 2 * GNC);
+  for (int g = 0; g < G; ++g) greb_build_wz(&wz[(size_t)g * 2 * GNC], h->F, h->phys[h->group_rep[g]]);
+  for (int m = 0; m < N; ++m) {
+    if (m == h->group_rep[h->group_of[m]]) {
+      greb_build_member_const(mc[m], h->phys[m], h->group_of[m]);
+      greb_build_initial_state(&state[(size_t)m * GS_COUNT * GNC], h->F, mc[m]);
+    } else {
+      const int r = h->group_rep[h->group_of[m]];
+      mc[m] = mc[r];
+      memcpy(&state[(size_t)m * GS_COUNT * GNC], &state[(size_t)r * GS_COUNT * GNC], GS_COUNT * GNC * 4);
+    }
+  }
+  h->co2_stride = 1;
+  for (int m = 0; m < N; ++m) h->co2_stride = std::max(h->co2_stride, (int)h->co2[m].size());
+  std::vector<float> co2((size_t)N * h->co2_stride, 680.f);
+  for (int m = 0; m < N; ++m)
+    for (size_t y = 0; y < h->co2[m].size(); ++y) co2[(size_t)m * h->co2_stride + y] = h->co2[m][y];
+  std::vector<int> ids_all(N);
+  for (int m = 0; m < N; ++m) ids_all[m] = m;
+
+  CK(upload(&h->d_forc, h->F.forc));
+  CK(upload(&h->d_sw, h->F.sw_solar));
+  CK(upload(&h->d_mask, h->F.mask));
+  CK(upload(&h->d_zoc, h->F.z_ocean));
+  CK(upload(&h->d_toclim, h->F.toclim));
+  CK(upload(&h->d_tclim, h->F.tclim));
+  CK(upload(&h->d_qclim, h->F.qclim));
+  CK(upload(&h->d_coslat, h->F.coslat_w));
+  CK(upload(&h->d_wz, wz));
+  CK(upload(&h->d_state, state));
+  CK(upload(&h->d_co2, co2));
+  CK(upload(&h->d_mc, mc));
+  CK(upload(&h->d_ids_all, ids_all));
+  CK(upload(&h->d_ids_rep, h->group_rep));
+  CK(cudaMalloc((void**)&h->d_corr, (size_t)G * GNT * GC_COUNT * GNC * 4));
+  CK(cudaMemset(h->d_corr, 0, (size_t)G * GNT * GC_COUNT * GNC * 4));
+  CK(cudaMalloc((void**)&h->d_acc, (size_t)N * GA_COUNT * GNC * 4));
+  CK(cudaMemset(h->d_acc, 0, (size_t)N * GA_COUNT * GNC * 4));
+  for (int i = 0; i < 2; ++i) {
+    CK(cudaMalloc((void**)&h->d_out[i], (size_t)N * 12 * 5 * GNC * 4));
+    CK(cudaMemset(h->d_out[i], 0, (size_t)N * 12 * 5 * GNC * 4));
+  }
+  CK(cudaMalloc((void**)&h->d_diag, (size_t)N * 2 * 4));
+  CK(cudaMemset(h->d_diag, 0, (size_t)N * 2 * 4));
+  CK(cudaMalloc((void**)&h->d_flags, (size_t)N * 4));
+  CK(cudaMemset(h->d_flags, 0, (size_t)N * 4));
+  h->it_next = 1;
+  h->inited = true;
+  return GREB_OK;
+}
+
+static GrebKernelArgs base_args(greb_b200_t h) {
+  GrebKernelArgs a;
+  memset(&a, 0, sizeof a);
+  a.mc = h->d_mc;
+  a.member_ids = h->d_ids_all;
+  a.forc = h->d_forc;
+  a.sw_solar = h->d_sw;
+  a.mask = h->d_mask;
+  a.z_ocean = h->d_zoc;
+  a.toclim = h->d_toclim;
+  a.tclim = h->d_tclim;
+  a.qclim = h->d_qclim;
+  a.wz = h->d_wz;
+  a.corr = h->d_corr;
+  a.state = h->d_state;
+  a.acc = h->d_acc;
+  a.out = nullptr;
+  a.co2 = h->d_co2;
+  a.diag = h->d_diag;
+  a.coslat_w = h->d_coslat;
+  a.flags = h->d_flags;
+  a.co2_stride = h->co2_stride;
+  a.out_months = 12;
+  return a;
+}
+
+extern "C" int greb_b200_spinup(greb_b200_t h, int years) {
+  if (!h) return GREB_E_INVALID;
+  if (!h->inited) return fail(h, GREB_E_INVALID, "greb_b200_spinup: greb_b200_init has not been called");
+  if (years < 0) return fail(h, GREB_E_INVALID, "greb_b200_spinup: years < 0");
+  cudaSetDevice(h->device);
+  const int G = (int)h->group_rep.size();
+  GrebKernelArgs a = base_args(h);
+  a.member_ids = h->d_ids_rep;
+  a.spinup = 1;
+  h->last_launches = 0;
+  CK(cudaEventRecord(h->ev0, h->stream));
+  for (int y = 0; y < years; ++y) {
+    a.it0 = 1 + y * GNT;
+    a.nsteps = GNT;
+    greb_member_kernel<<<G, GREB_NTHREADS, GREB_SMEM_BYTES, h->stream>>>(a);
+    h->last_launches++;
+  }
+  CK(cudaEventRecord(h->ev1, h->stream));
+  CK(cudaGetLastError());
+  // the spin-up end state of a group's representative is the start state of all its members (f:361, f:226)
+  for (int m = 0; m < h->n_members; ++m) {
+    const int r = h->group_rep[h->group_of[m]];
+    if (r != m)
+      CK(cudaMemcpyAsync(h->d_state + (size_t)m * GS_COUNT * GNC, h->d_state + (size_t)r * GS_COUNT * GNC,
+                         GS_COUNT * GNC * 4, cudaMemcpyDeviceToDevice, h->stream));
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+  return GREB_OK;
+}
+
+extern "C" int greb_b200_reset_scenario(greb_b200_t h) {
+  if (!h) return GREB_E_INVALID;
+  if (!h->inited) return fail(h, GREB_E_INVALID, "greb_b200_reset_scenario: not initialised");
+  cudaSetDevice(h->device);
+  // f:227: year=year0, mon=1, irec=0, monthly accumulators zero (tsmn is zero after whole years)
+  CK(cudaMemsetAsync(h->d_acc, 0, (size_t)h->n_members * GA_COUNT * GNC * 4, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->it_next = 1;
+  return GREB_OK;
+}
+
+extern "C" int greb_b200_run(greb_b200_t h, int years, float* out, const int* out_members, int n_out, float* gmean,
+                             float* gmean_coslat) {
+  if (!h) return GREB_E_INVALID;
+  if (!h->inited) return fail(h, GREB_E_INVALID, "greb_b200_run: greb_b200_init has not been called");
+  if (years < 0) return fail(h, GREB_E_INVALID, "greb_b200_run: years < 0");
+  if ((h->it_next - 1) % GNT != 0) return fail(h, GREB_E_INVALID, "greb_b200_run: not at a year boundary");
+  const int N = h->n_members;
+  const int y_first = (h->it_next - 1) / GNT;
+  if (y_first + years > h->co2_stride)
+    return fail(h, GREB_E_INVALID, "greb_b200_run: the CO2 paths given to set_member are shorter than the run");
+  if (!out_members) n_out = N;
+  cudaSetDevice(h->device);
+  GrebKernelArgs a = base_args(h);
+  a.spinup = 0;
+  const size_t year_floats = (size_t)12 * 5 * GNC;
+  std::vector<float> diag((size_t)N * 2);
+  h->last_launches = 0;
+  CK(cudaEventRecord(h->ev0, h->stream));
+  for (int y = 0; y < years; ++y) {
+    const int b = y & 1;
+    a.it0 = h->it_next;
+    a.nsteps = GNT;
+    a.out = h->d_out[b];
+    if (y >= 2 && out) CK(cudaStreamWaitEvent(h->stream, h->ev_c[b], 0));  // buffer b free again
+    greb_member_kernel<<<N, GREB_NTHREADS, GREB_SMEM_BYTES, h->stream>>>(a);
+    h->last_launches++;
+    CK(cudaGetLastError());
+    h->it_next += GNT;
+    h->last_out = b;
+    if (y == years - 1) CK(cudaEventRecord(h->ev1, h->stream));
+    if (out) {
+      CK(cudaEventRecord(h->ev_k[b], h->stream));
+      CK(cudaStreamWaitEvent(h->copy_stream, h->ev_k[b], 0));
+      if (!out_members) {
+        CK(cudaMemcpy2DAsync(out + (size_t)y * year_floats, (size_t)years * year_floats * 4, h->d_out[b],
+                             year_floats * 4, year_floats * 4, N, cudaMemcpyDeviceToHost, h->copy_stream));
+      } else {
+        for (int i = 0; i < n_out; ++i) {
+          const int m = out_members[i];
+          if (m < 0 || m >= N) return fail(h, GREB_E_INVALID, "greb_b200_run: out_members entry out of range");
+          CK(cudaMemcpyAsync(out + ((size_t)i * years + y) * year_floats, h->d_out[b] + (size_t)m * year_floats,
+                             year_floats * 4, cudaMemcpyDeviceToHost, h->copy_stream));
+        }
+      }
+      CK(cudaEventRecord(h->ev_c[b], h->copy_stream));
+    }
+    if (gmean || gmean_coslat) {
+      CK(cudaMemcpyAsync(diag.data(), h->d_diag, diag.size() * 4, cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+      for (int m = 0; m < N; ++m) {
+        if (gmean) gmean[(size_t)m * years + y] = diag[(size_t)m * 2];
+        if (gmean_coslat) gmean_coslat[(size_t)m * years + y] = diag[(size_t)m * 2 + 1];
+      }
+    }
+  }
+  if (years == 0) CK(cudaEventRecord(h->ev1, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaStreamSynchronize(h->copy_stream));
+  CK(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+  return GREB_OK;
+}
+
+extern "C" int greb_b200_time_loop(greb_b200_t h, int it) {
+  if (!h) return GREB_E_INVALID;
+  if (!h->inited) return fail(h, GREB_E_INVALID, "greb_b200_time_loop: not initialised");
+  if (it < 1 || (it - 1) / GNT >= h->co2_stride) return fail(h, GREB_E_INVALID, "greb_b200_time_loop: bad it");
+  cudaSetDevice(h->device);
+  GrebKernelArgs a = base_args(h);
+  a.spinup = 0;
+  a.it0 = it;
+  a.nsteps = 1;
+  a.out = h->d_out[0];
+  h->last_out = 0;
+  greb_member_kernel<<<h->n_members, GREB_NTHREADS, GREB_SMEM_BYTES, h->stream>>>(a);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));
+  h->it_next = it + 1;
+  return GREB_OK;
+}
+
+extern "C" int greb_b200_get_state(greb_b200_t h, int member, int which, float* out) {
+  if (!h) return GREB_E_INVALID;
+  if (!h->inited || member < 0 || member >= h->n_members || which < 0 || which >= GS_COUNT || !out)
+    return fail(h, GREB_E_INVALID, "greb_b200_get_state: bad arguments");
+  cudaSetDevice(h->device);
+  CK(cudaMemcpy(out, h->d_state + ((size_t)member * GS_COUNT + which) * GNC, GNC * 4, cudaMemcpyDeviceToHost));
+  return GREB_OK;
+}
+
+extern "C" int greb_b200_set_state(greb_b200_t h, int member, int which, const float* in) {
+  if (!h) return GREB_E_INVALID;
+  if (!h->inited || member < 0 || member >= h->n_members || which < 0 || which >= GS_COUNT || !in)
+    return fail(h, GREB_E_INVALID, "greb_b200_set_state: bad arguments");
+  cudaSetDevice(h->device);
+  CK(cudaMemcpy(h->d_state + ((size_t)member * GS_COUNT + which) * GNC, in, GNC * 4, cudaMemcpyHostToDevice));
+  return GREB_OK;
+}
+
+extern "C" int greb_b200_get_states(greb_b200_t h, float* out) {
+  if (!h) return GREB_E_INVALID;
+  if (!h->inited || !out) return fail(h, GREB_E_INVALID, "greb_b200_get_states: bad arguments");
+  cudaSetDevice(h->device);
+  CK(cudaMemcpyAsync(out, h->d_state, (size_t)h->n_members * GS_COUNT * GNC * 4, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return GREB_OK;
+}
+
+extern "C" int greb_b200_set_states(greb_b200_t h, const float* in) {
+  if (!h) return GREB_E_INVALID;
+  if (!h->inited || !in) return fail(h, GREB_E_INVALID, "greb_b200_set_states: bad arguments");
+  cudaSetDevice(h->device);
+  CK(cudaMemcpyAsync(h->d_state, in, (size_t)h->n_members * GS_COUNT * GNC * 4, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return GREB_OK;
+}
+
+extern "C" int greb_b200_get_fluxcorr(greb_b200_t h, int member, int which, float* out) {
+  if (!h) return GREB_E_INVALID;
+  if (!h->inited || member < 0 || member >= h->n_members || which < 0 || which > 2 || !out)
+    return fail(h, GREB_E_INVALID, "greb_b200_get_fluxcorr: bad arguments");
+  cudaSetDevice(h->device);
+  static const int sel[3] = {GC_TF, GC_QF, GC_TOF};  // ABI order: TF, qF, ToF
+  const float* base = h->d_corr + (size_t)h->group_of[member] * GNT * GC_COUNT * GNC + (size_t)sel[which] * GNC;
+  CK(cudaMemcpy2D(out, GNC * 4, base, (size_t)GC_COUNT * GNC * 4, GNC * 4, GNT, cudaMemcpyDeviceToHost));
+  return GREB_OK;
+}
+
+extern "C" int greb_b200_get_monthly(greb_b200_t h, int member, float* out) {
+  if (!h) return GREB_E_INVALID;
+  if (!h->inited || member < 0 || member >= h->n_members || !out)
+    return fail(h, GREB_E_INVALID, "greb_b200_get_monthly: bad arguments");
+  cudaSetDevice(h->device);
+  CK(cudaMemcpy(out, h->d_out[h->last_out] + (size_t)member * 12 * 5 * GNC, (size_t)12 * 5 * GNC * 4,
+                cudaMemcpyDeviceToHost));
+  return GREB_OK;
+}
+
+extern "C" int greb_b200_diag_device(greb_b200_t h, const float** dev_ptr, int* n_floats) {
+  if (!h) return GREB_E_INVALID;
+  if (!h->inited || !dev_ptr || !n_floats) return fail(h, GREB_E_INVALID, "greb_b200_diag_device: bad arguments");
+  *dev_ptr = h->d_diag;
+  *n_floats = h->n_members * 2;
+  return GREB_OK;
+}
+
+extern "C" int greb_b200_get_flags(greb_b200_t h, int* flags) {
+  if (!h) return GREB_E_INVALID;
+  if (!h->inited || !flags) return fail(h, GREB_E_INVALID, "greb_b200_get_flags: bad arguments");
+  cudaSetDevice(h->device);
+  CK(cudaMemcpy(flags, h->d_flags, (size_t)h->n_members * 4, cudaMemcpyDeviceToHost));
+  return GREB_OK;
+}
+
+extern "C" int greb_b200_circulation(greb_b200_t h, int member, int ityr, const float* X_in, const float* wz,
+                                     float* dX_crcl, int n) {
+  if (!h) return GREB_E_INVALID;
+  if (!h->inited || member < 0 || member >= h->n_members || ityr < 1 || ityr > GNT || !X_in || !wz || !dX_crcl ||
+      n < 1)
+    return fail(h, GREB_E_INVALID, "greb_b200_circulation: bad arguments");
+  cudaSetDevice(h->device);
+  float *dX = nullptr, *dW = nullptr, *dO = nullptr;
+  const size_t bytes = (size_t)n * GNC * 4;
+  CK(cudaMalloc((void**)&dX, bytes));
+  CK(cudaMalloc((void**)&dW, bytes));
+  CK(cudaMalloc((void**)&dO, bytes));
+  CK(cudaMemcpy(dX, X_in, bytes, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dW, wz, bytes, cudaMemcpyHostToDevice));
+  GrebCirculationArgs a;
+  a.mc = h->d_mc + member;
+  a.uv = h->d_forc + (size_t)(ityr - 1) * GF_COUNT * GNC + GF_U * GNC;  // GF_U, GF_V are adjacent
+  a.X_in = dX;
+  a.wz = dW;
+  a.dX = dO;
+  CK(cudaEventRecord(h->ev0, h->stream));
+  greb_circulation_kernel<<<n, GREB_NTHREADS, GREB_SMEM_BYTES, h->stream>>>(a);
+  CK(cudaEventRecord(h->ev1, h->stream));
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+  h->last_launches = 1;
+  CK(cudaMemcpy(dX_crcl, dO, bytes, cudaMemcpyDeviceToHost));
+  cudaFree(dX);
+  cudaFree(dW);
+  cudaFree(dO);
+  return GREB_OK;
+}
+
+extern "C" int greb_b200_last_kernel_ms(greb_b200_t h, float* ms, int* launches) {
+  if (!h) return GREB_E_INVALID;
+  if (ms) *ms = h->last_ms;
+  if (launches) *launches = h->last_launches;
+  return GREB_OK;
+}

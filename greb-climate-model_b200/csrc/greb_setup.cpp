@@ -1,0 +1,242 @@
+// greb_setup.cpp — see greb_setup.h.  Reference: /root/reference/src/greb.f90 ("f:NNN").
+#include "greb_setup.h"
+
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+
+void greb_b200_physics_defaults(greb_physics_par* p) {  // f:68-104
+  static const float pe[10] = {9.0721f, 106.7252f, 61.5562f, 0.0179f, 0.0028f,
+                               0.0570f, 0.3462f, 2.3406f, 0.7032f, 1.0662f};
+  p->pi = 3.1416f;
+  p->sig = 5.6704e-8f;
+  p->rho_ocean = 999.1f;
+  p->rho_land = 2600.f;
+  p->rho_air = 1.2f;
+  p->cp_ocean = 4186.f;
+  p->cp_land = 926.222f;
+  p->cp_air = 1005.f;
+  p->eps = 1.f;
+  p->d_ocean = 50.f;
+  p->d_land = 2.f;
+  p->d_air = 5000.f;
+  p->ct_sens = 22.5f;
+  p->da_ice = 0.25f;
+  p->a_no_ice = 0.1f;
+  p->a_cloud = 0.35f;
+  p->Tl_ice1 = 273.15f - 10.f;
+  p->Tl_ice2 = 273.15f;
+  p->To_ice1 = 273.15f - 7.f;
+  p->To_ice2 = 273.15f - 1.7f;
+  p->co_turb = 5.0f;
+  p->kappa = 8e5f;
+  p->ce = 2e-3f;
+  p->cq_latent = 2.257e6f;
+  p->cq_rain = -0.1f / 24.f / 3600.f;
+  p->z_air = 8400.f;
+  p->z_vapor = 5000.f;
+  p->r_qviwv = 2.6736e3f;
+  memcpy(p->p_emi, pe, sizeof pe);
+  p->co2_flux = 298.f;
+}
+
+void greb_b200_physics_original(greb_physics_par* p) {  // src/greb.original.model.f90:63-101, :178
+  greb_b200_physics_defaults(p);
+  p->cp_land = p->cp_ocean / 4.5f;
+  p->co2_flux = 340.f;
+}
+
+void greb_b200_pad_co2(const float* given, int n_given, float* co2, int n_years) {  // f:1047-1061
+  for (int i = 0; i < n_years; ++i) co2[i] = (i < n_given) ? given[i] : -1.f;
+  if (n_years > 0 && co2[0] == -1.f) co2[0] = 680.f;
+  for (int i = 1; i < n_years; ++i)
+    if (co2[i] < 0.f) {
+      for (int j = i; j < n_years; ++j) co2[j] = co2[i - 1];
+      break;
+    }
+}
+
+bool greb_physics_equal(const greb_physics_par& a, const greb_physics_par& b) {
+  return memcmp(&a, &b, sizeof(greb_physics_par)) == 0;
+}
+
+void greb_build_forcing(GrebHostForcing& F, const float* z_topo, const float* glacier, const float* sw_solar,
+                        const float* tclim, const float* qclim, const float* swetclim, const float* uclim,
+                        const float* vclim, const float* mldclim, const float* cldclim) {
+  F.forc.assign((size_t)GNT * GF_COUNT * GNC, 0.f);
+  F.sw_solar.assign(sw_solar, sw_solar + (size_t)GNT * GY);
+  F.z_topo.assign(z_topo, z_topo + GNC);
+  F.tclim.assign(tclim, tclim + (size_t)GNT * GNC);
+  F.qclim.assign(qclim, qclim + (size_t)GNT * GNC);
+  F.mld0.assign(mldclim, mldclim + GNC);
+  F.mask.assign(GNC, 0);
+  F.z_ocean.assign(GNC, 0.f);
+  F.toclim.assign(GNC, 0.f);
+  for (int c = 0; c < GNC; ++c) {
+    int m = 0;
+    if (z_topo[c] >= 0.f) m |= GM_TOPO_GE0;  // f:384
+    if (z_topo[c] < 0.f) m |= GM_TOPO_LT0;   // f:389, 483, 511
+    if (glacier[c] > 0.5f) m |= GM_GLACIER;  // f:395, 490
+    F.mask[c] = m;
+    // f:1087-1094 Toclim
+    float mn = tclim[c];
+    for (int n = 1; n < GNT; ++n) mn = std::min(mn, tclim[(size_t)n * GNC + c]);
+    if (mn - 273.15f < -1.7f) mn = -1.7f + 273.15f;
+    F.toclim[c] = mn;
+    // f:179-183 z_ocean
+    float zo = 0.f;
+    for (int n = 0; n < GNT; ++n)
+      if (mldclim[(size_t)n * GNC + c] > zo) zo = mldclim[(size_t)n * GNC + c];
+    F.z_ocean[c] = 3.0f * zo;
+  }
+  for (int n = 0; n < GNT; ++n) {
+    float* rec = &F.forc[(size_t)n * GF_COUNT * GNC];
+    const int np = (n > 0) ? n - 1 : GNT - 1;  // f:507-508
+    for (int c = 0; c < GNC; ++c) {
+      const size_t i = (size_t)n * GNC + c;
+      const float u = uclim[i], v = vclim[i];
+      rec[GF_U * GNC + c] = u;
+      rec[GF_V * GNC + c] = v;
+      rec[GF_CLD * GNC + c] = cldclim[i];
+      rec[GF_DTRAD * GNC + c] = -0.16f * tclim[i] - 5.f;  // f:176
+      rec[GF_SWET * GNC + c] = swetclim[i];
+      float aw = sqrtf(u * u + v * v);                                // f:452
+      if (z_topo[c] > 0.f) aw = sqrtf(aw * aw + 2.0f * 2.0f);          // f:453
+      if (z_topo[c] < 0.f) aw = sqrtf(aw * aw + 3.0f * 3.0f);          // f:454
+      rec[GF_ABSWIND * GNC + c] = aw;
+      rec[GF_MLD * GNC + c] = mldclim[i];
+      rec[GF_DMLD * GNC + c] = mldclim[i] - mldclim[(size_t)np * GNC + c];
+    }
+  }
+  // cos-lat weights of the README's global mean (README.md:36-37), normalised
+  F.coslat_w.resize(GY);
+  double s = 0;
+  for (int k = 0; k < GY; ++k) {
+    const double lat = (k + 0.5) * 3.75 - 90.0;
+    F.coslat_w[k] = (float)cos(lat * 3.14159265358979323846 / 180.0);
+    s += F.coslat_w[k];
+  }
+  for (int k = 0; k < GY; ++k) F.coslat_w[k] = (float)(F.coslat_w[k] / s);
+}
+
+static int f_nint(float x) { return (int)lroundf(x); }
+
+void greb_partition_rows(const int* polar, const int* time2_diff, const int* time2_adv, int* row0, int* nrow) {
+  // issue-slot model per cell and sub-step: main row 51, polar row 61, +25 per extra
+  // diffusion sub-sub-step, +22 per extra advection sub-sub-step
+  int cost[GY];
+  for (int k = 0; k < GY; ++k)
+    cost[k] = (polar[k] ? 61 : 51) + 25 * (time2_diff[k] - 1) + 22 * (time2_adv[k] - 1);
+  // DP: split rows 0..47 into GREB_NWARP contiguous bands of 1..GREB_MAXR rows minimising the
+  // sum of squared band costs
+  const double INF = 1e300;
+  static double best[GREB_NWARP + 1][GY + 1];
+  static int from[GREB_NWARP + 1][GY + 1];
+  for (int b = 0; b <= GREB_NWARP; ++b)
+    for (int k = 0; k <= GY; ++k) best[b][k] = INF;
+  best[0][0] = 0;
+  for (int b = 1; b <= GREB_NWARP; ++b)
+    for (int k = 1; k <= GY; ++k)
+      for (int n = 1; n <= GREB_MAXR && n <= k; ++n) {
+        if (best[b - 1][k - n] >= INF) continue;
+        double c = 0;
+        for (int j = k - n; j < k; ++j) c += cost[j];
+        const double v = best[b - 1][k - n] + c * c;
+        if (v < best[b][k]) {
+          best[b][k] = v;
+          from[b][k] = n;
+        }
+      }
+  int b0[GREB_NWARP], bn[GREB_NWARP], bc[GREB_NWARP];
+  for (int b = GREB_NWARP, k = GY; b >= 1; --b) {
+    const int n = from[b][k];
+    bn[b - 1] = n;
+    b0[b - 1] = k - n;
+    k -= n;
+  }
+  for (int b = 0; b < GREB_NWARP; ++b) {
+    bc[b] = 0;
+    for (int j = b0[b]; j < b0[b] + bn[b]; ++j) bc[b] += cost[j];
+  }
+  // bands -> warps: longest-processing-time first into the 4 sub-partitions, 3 warps each
+  int order[GREB_NWARP];
+  for (int b = 0; b < GREB_NWARP; ++b) order[b] = b;
+  std::stable_sort(order, order + GREB_NWARP, [&](int x, int y) { return bc[x] > bc[y]; });
+  int load[4] = {0, 0, 0, 0}, cnt[4] = {0, 0, 0, 0};
+  for (int i = 0; i < GREB_NWARP; ++i) {
+    int bestq = -1;
+    for (int q = 0; q < 4; ++q)
+      if (cnt[q] < GREB_NWARP / 4 && (bestq < 0 || load[q] < load[bestq])) bestq = q;
+    const int w = bestq + 4 * cnt[bestq];
+    row0[w] = b0[order[i]];
+    nrow[w] = bn[order[i]];
+    load[bestq] += bc[order[i]];
+    cnt[bestq]++;
+  }
+}
+
+void greb_build_member_const(GrebMemberConst& mc, const greb_physics_par& p, int group) {
+  memset(&mc, 0, sizeof mc);
+  mc.sig = p.sig; mc.ct_sens = p.ct_sens; mc.da_ice = p.da_ice; mc.a_no_ice = p.a_no_ice; mc.a_cloud = p.a_cloud;
+  mc.Tl_ice1 = p.Tl_ice1; mc.Tl_ice2 = p.Tl_ice2; mc.To_ice1 = p.To_ice1; mc.To_ice2 = p.To_ice2;
+  mc.co_turb = p.co_turb; mc.ce = p.ce; mc.cq_latent = p.cq_latent; mc.cq_rain = p.cq_rain;
+  mc.rho_air = p.rho_air; mc.r_qviwv = p.r_qviwv;
+  memcpy(mc.p_emi, p.p_emi, sizeof mc.p_emi);
+  mc.cap_ocean = p.cp_ocean * p.rho_ocean;          // f:186
+  mc.cap_land = p.cp_land * p.rho_land * p.d_land;  // f:187
+  mc.cap_air = p.cp_air * p.rho_air * p.d_air;      // f:188
+  mc.co2_flux = p.co2_flux;
+  mc.group = group;
+  // geometry, f:578-582 / f:749-753 (the reference recomputes it in every call)
+  const float DT_CRCL = 1800.0f, DLON = 3.75f, DLAT = 3.75f;
+  const float pi = p.pi, kappa = p.kappa;
+  const float deg = 2.f * pi * 6.371e6f / 360.f;
+  const float dyy = DLAT * deg;
+  mc.ccy_diff = kappa * DT_CRCL / (dyy * dyy);
+  mc.ccy_adv = DT_CRCL / dyy / 2.f;
+  for (int k = 1; k <= GY; ++k) {
+    const float lat = DLAT * (float)k - DLAT / 2.f - 90.f;
+    const float dxlat = DLON * deg * cosf(2.f * pi / 360.f * lat);
+    mc.ccx_diff[k - 1] = kappa * DT_CRCL / (dxlat * dxlat);
+    mc.ccx_adv[k - 1] = DT_CRCL / dxlat / 2.f;
+    mc.polar[k - 1] = !(dxlat > 2.5e5f);  // f:592, 799
+    {                                     // f:652-654
+      const int n = f_nint(DT_CRCL / (1.f * (dxlat * dxlat) / kappa));
+      const float dd = (float)std::max(1, n);
+      const int dtdff2 = (int)(DT_CRCL / dd);
+      mc.time2_diff[k - 1] = std::max(1, f_nint(DT_CRCL / (float)dtdff2));
+      mc.ccx2_diff[k - 1] = kappa * (float)dtdff2 / (dxlat * dxlat);
+    }
+    {  // f:838-840
+      const int n = f_nint(DT_CRCL / (dxlat / 10.0f / 1.f));
+      const float dd = (float)std::max(1, n);
+      const int dtdff2 = (int)(DT_CRCL / dd);
+      mc.time2_adv[k - 1] = std::max(1, f_nint(DT_CRCL / (float)dtdff2));
+      mc.ccx2_adv[k - 1] = (float)dtdff2 / dxlat / 2.f;
+    }
+  }
+  greb_partition_rows(mc.polar, mc.time2_diff, mc.time2_adv, mc.row0, mc.nrow);
+}
+
+void greb_build_wz(float* out, const GrebHostForcing& F, const greb_physics_par& p) {
+  for (int c = 0; c < GNC; ++c) {
+    out[c] = expf(-F.z_topo[c] / p.z_air);          // f:201 (== exp(-z_topo/z_air) of f:420, 458)
+    out[GNC + c] = expf(-F.z_topo[c] / p.z_vapor);  // f:202
+  }
+}
+
+void greb_build_initial_state(float* out, const GrebHostForcing& F, const GrebMemberConst& mc) {
+  const float* t_last = &F.tclim[(size_t)(GNT - 1) * GNC];
+  const float* q_last = &F.qclim[(size_t)(GNT - 1) * GNC];
+  for (int c = 0; c < GNC; ++c) {
+    out[GS_TS * GNC + c] = t_last[c];       // f:194
+    out[GS_TA * GNC + c] = t_last[c];       // f:195
+    out[GS_TO * GNC + c] = F.toclim[c];     // f:196
+    out[GS_Q * GNC + c] = q_last[c];        // f:197
+    float cap = 0.f;                        // f:190-191
+    if (F.z_topo[c] > 0.f) cap = mc.cap_land;
+    if (F.z_topo[c] <= 0.f) cap = mc.cap_ocean * F.mld0[c];
+    out[GS_CAP * GNC + c] = cap;
+  }
+}

@@ -1,0 +1,76 @@
+// greb_types.h — plain-old-data shared by the host runtime and the kernels.
+#pragma once
+
+#define GX 96           // longitudes (reference src/greb.f90:36 xdim)
+#define GY 48           // latitudes  (ydim)
+#define GNC (GX * GY)   // cells per field
+#define GNT 730         // steps per year (nstep_yr, :41)
+#define GSUB 24         // circulation sub-steps per step: nint(43200/1800) (:543)
+
+#define GREB_NWARP 12   // warps per member CTA
+#define GREB_MAXR 5     // max latitude rows owned by one warp
+#define GREB_NTHREADS (GREB_NWARP * 32)
+
+// per-step shared forcing record: forc[ityr][GF_*][GNC]
+enum { GF_U = 0, GF_V, GF_CLD, GF_DTRAD, GF_SWET, GF_ABSWIND, GF_MLD, GF_DMLD, GF_COUNT };
+// flux corrections: corr[group][ityr][GC_*][GNC]   (src/greb.f90:110)
+enum { GC_TF = 0, GC_TOF, GC_QF, GC_COUNT };
+// state[member][GS_*][GNC]
+enum { GS_TS = 0, GS_TA, GS_TO, GS_Q, GS_CAP, GS_COUNT };
+// acc[member][GA_*][GNC]: the five monthly accumulators (:149) + annual Tsurf accumulator tsmn (:145)
+enum { GA_TMM = 0, GA_TAMM, GA_TOMM, GA_QMM, GA_APMM, GA_TSMN, GA_COUNT };
+// static mask bits (the reference's three different land/ocean predicates)
+enum { GM_TOPO_GE0 = 1, GM_TOPO_LT0 = 2, GM_GLACIER = 4 };
+
+struct GrebMemberConst {
+  // physics scalars used on the device (namelist physics_par, src/greb.f90:68-104)
+  float sig, ct_sens, da_ice, a_no_ice, a_cloud, Tl_ice1, Tl_ice2, To_ice1, To_ice2;
+  float co_turb, ce, cq_latent, cq_rain, rho_air, r_qviwv;
+  float p_emi[10];
+  float cap_ocean, cap_land, cap_air;  // :186-188
+  float co2_flux;
+  // circulation geometry (:578-582, 652-654, 749-753, 838-840), computed on the host with the
+  // same libm the reference links, so the device never evaluates cos()
+  float ccy_diff, ccy_adv;
+  float ccx_diff[GY], ccx_adv[GY], ccx2_diff[GY], ccx2_adv[GY];
+  int polar[GY], time2_diff[GY], time2_adv[GY];
+  // row ownership: warp w owns rows [row0[w], row0[w]+nrow[w])
+  int row0[GREB_NWARP], nrow[GREB_NWARP];
+  int group;  // physics group (shares wz fields and flux corrections)
+  int pad_[3];
+};
+
+struct GrebKernelArgs {
+  const GrebMemberConst* mc;  // [n_members]
+  const int* member_ids;      // [gridDim.x] member handled by each CTA
+  const float* forc;          // [730][GF_COUNT][GNC]
+  const float* sw_solar;      // [730][48]
+  const int* mask;            // [GNC]
+  const float* z_ocean;       // [GNC]
+  const float* toclim;        // [GNC]
+  const float* tclim;         // [730][GNC] (spin-up target)
+  const float* qclim;         // [730][GNC]
+  const float* wz;            // [n_groups][2][GNC]: wz_air, wz_vapor
+  float* corr;                // [n_groups][730][GC_COUNT][GNC]
+  float* state;               // [n_members][GS_COUNT][GNC]
+  float* acc;                 // [n_members][GA_COUNT][GNC]
+  float* out;                 // [n_members][out_months][5][GNC] monthly means of this launch (may be null)
+  const float* co2;           // [n_members][co2_stride] annual CO2 path
+  float* diag;                // [n_members][2]: {unweighted, cos-lat} annual-mean Tsurf [deg C]
+  const float* coslat_w;      // [48] normalised cos-lat weights
+  int* flags;                 // [n_members] non-finite flag
+  int co2_stride;
+  int out_months;             // capacity of `out` in months per member
+  int it0;                    // first step counter `it` (1-based) of this launch
+  int nsteps;
+  int spinup;                 // 1 = qflux_correction step (:325-362), 0 = time_loop (:239-274)
+};
+
+// kernel-level circulation entry
+struct GrebCirculationArgs {
+  const GrebMemberConst* mc;  // one member's constants
+  const float* uv;            // [2][GNC] u, v of the requested step
+  const float* X_in;          // [n][GNC]
+  const float* wz;            // [n][GNC]
+  float* dX;                  // [n][GNC]
+};

@@ -1,0 +1,150 @@
+/*
+ * greb_b200.h — C ABI of the B200-native GREB time-stepping core.
+ *
+ * This is the drop-in boundary for the reference's hot path.  The
+ * reference (sieste/greb-climate-model, Fortran 90) has no FFI layer: its boundary is a set of
+ * external subroutines over `real(xdim,ydim)` arrays plus module globals.  Each entry point
+ * below names the reference interface it replaces (file:line under the reference root); the
+ * Fortran ISO_C_BINDING stub a maintainer would add is in INTEGRATION.md and
+ * greb-climate-model_b200/fortran/greb_b200_host.f90.
+ *
+ * Conventions
+ *   - Plain C: opaque handle, pointers, sizes.  No C++/torch types.
+ *   - Every function returns 0 on success, a negative GREB_E_* code on failure; the message is
+ *     available from greb_b200_last_error().  Nothing calls exit().
+ *   - Arrays are the reference's own memory layout, no transposes: Fortran X(i,j[,n]) ==
+ *     C X[n][j][i], i = longitude fastest (96), j = latitude (48), n = step of year (730);
+ *     sw_solar(j,n) == [n][j].  All data are IEEE fp32.
+ *   - Host pointers unless the name says _device.  The library owns all device memory behind the
+ *     handle and keeps no caller pointer after a call returns.
+ *   - One handle drives one GPU.  Calls on one handle are not thread-safe; distinct handles are.
+ *   - There is no CPU fallback: every compute entry point fails with GREB_E_NO_DEVICE when no
+ *     sm_100 device is usable.
+ */
+#ifndef GREB_B200_H
+#define GREB_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GREB_XDIM 96
+#define GREB_YDIM 48
+#define GREB_NSTEP_YR 730
+#define GREB_NCELL (GREB_XDIM * GREB_YDIM)
+#define GREB_NVAR_OUT 5 /* Tsurf, Tair, Tocean, q, albedo: reference src/greb.f90:978-982 */
+
+enum {
+  GREB_OK = 0,
+  GREB_E_INVALID = -1,   /* bad argument / call order */
+  GREB_E_NO_DEVICE = -2, /* no usable sm_100 GPU (there is no CPU fallback) */
+  GREB_E_CUDA = -3,      /* CUDA runtime error, see greb_b200_last_error */
+  GREB_E_NOMEM = -4,
+  GREB_E_NONFINITE = -5  /* a member produced a non-finite state */
+};
+
+/* The reference's namelist physics_par (src/greb.f90:68-104,128-132) plus co2_flux of
+ * namelist co2_par (:104,134).  One block per ensemble member.  greb_b200_physics_defaults fills
+ * the reference defaults; greb_b200_physics_original fills greb.original.model.f90:63-101 with
+ * CO2_ctrl=340 (:178). */
+typedef struct greb_physics_par {
+  float pi, sig, rho_ocean, rho_land, rho_air, cp_ocean, cp_land, cp_air, eps;
+  float d_ocean, d_land, d_air, ct_sens, da_ice, a_no_ice, a_cloud;
+  float Tl_ice1, Tl_ice2, To_ice1, To_ice2, co_turb, kappa, ce, cq_latent, cq_rain;
+  float z_air, z_vapor, r_qviwv;
+  float p_emi[10];
+  float co2_flux;
+} greb_physics_par;
+
+typedef struct greb_b200_handle_s* greb_b200_t;
+
+/* ---- lifecycle ----------------------------------------------------------------------------- */
+
+void greb_b200_physics_defaults(greb_physics_par* p);
+void greb_b200_physics_original(greb_physics_par* p);
+
+/* Creates a context for `n_members` independent ensemble members on CUDA device `device`.
+ * Replaces: one `./greb <namelist>` OS process per member (src/greb.f90:1030-1038, 1063-1068). */
+int greb_b200_create(greb_b200_t* h, int n_members, int device);
+int greb_b200_destroy(greb_b200_t h);
+const char* greb_b200_last_error(greb_b200_t h); /* h may be NULL: last create() error */
+int greb_b200_n_members(greb_b200_t h);
+
+/* ---- inputs -------------------------------------------------------------------------------- */
+
+/* The ten input fields PROGRAM greb_run reads (src/greb.f90:1073-1085) — shared by all members.
+ * Toclim is derived inside exactly as src/greb.f90:1087-1094.  Copies to the device once. */
+int greb_b200_set_forcing(greb_b200_t h, const float* z_topo /*[48][96]*/, const float* glacier /*[48][96]*/,
+                          const float* sw_solar /*[730][48]*/, const float* tclim /*[730][48][96]*/,
+                          const float* qclim, const float* swetclim, const float* uclim, const float* vclim,
+                          const float* mldclim, const float* cldclim);
+
+/* Per-member namelist values: physics_par (+co2_flux) and the CO2 path of co2_par already
+ * padded to n_years entries the way src/greb.f90:1053-1061 pads it (greb_b200_pad_co2 does it).
+ * Members with identical physics share one flux-correction spin-up. */
+int greb_b200_set_member(greb_b200_t h, int member, const greb_physics_par* p, const float* co2_ppm, int n_years,
+                         int year0);
+/* src/greb.f90:1047-1061: `n_given` values followed by padding to n_years (first<0 -> 680). */
+void greb_b200_pad_co2(const float* given, int n_given, float* co2_ppm, int n_years);
+
+/* ---- model run ----------------------------------------------------------------------------- */
+
+/* greb_model preamble (src/greb.f90:176-216): derived fields, heat capacities, initial state
+ * (step 730 of the climatology), wz_*, geometry of the circulation sub-steps.  Call after
+ * set_forcing and all set_member calls. */
+int greb_b200_init(greb_b200_t h);
+
+/* qflux_correction (src/greb.f90:311-364): `years` years at each member's co2_flux; leaves the
+ * flux corrections on the device and the members in the spin-up end state (:361). */
+int greb_b200_spinup(greb_b200_t h, int years);
+
+/* Scenario loop (src/greb.f90:226-234), `years` more years for every member, continuing the
+ * calendar (call greb_b200_reset_scenario first for the :227 reset).  For each simulated year
+ * the 12x5 monthly-mean records of every member are produced on the device; if `out` is not
+ * NULL they are copied to host as out[member][year][month][var][lat][lon] (the reference's
+ * record stream of unit 22, :978-982, per member); `out_members` (may be NULL = all) lists the
+ * `n_out` members to copy.  gmean (may be NULL) receives [member][year] the console value
+ * sum(tsmn)/(xdim*ydim)-273.15 (:954); gmean_coslat (may be NULL) the cos-lat weighted annual
+ * mean Tsurf in deg C (README.md:36-37). */
+int greb_b200_reset_scenario(greb_b200_t h);
+int greb_b200_run(greb_b200_t h, int years, float* out, const int* out_members, int n_out, float* gmean,
+                  float* gmean_coslat);
+
+/* One time_loop call (src/greb.f90:239-274) for every member with step counter `it` (1-based,
+ * as the reference's `it`).  Test entry: lets a host drive the loop step by step. */
+int greb_b200_time_loop(greb_b200_t h, int it);
+
+/* ---- state / results access ---------------------------------------------------------------- */
+
+enum { GREB_TS = 0, GREB_TA = 1, GREB_TO = 2, GREB_Q = 3, GREB_CAP = 4 };
+int greb_b200_get_state(greb_b200_t h, int member, int which, float* out /*[48][96]*/);
+int greb_b200_set_state(greb_b200_t h, int member, int which, const float* in);
+/* bulk variants: all members at once, [n_members][5][48][96] in the order of the enum above */
+int greb_b200_get_states(greb_b200_t h, float* out);
+int greb_b200_set_states(greb_b200_t h, const float* in);
+/* which: 0 = TF_correct, 1 = qF_correct, 2 = ToF_correct (src/greb.f90:110), out [730][48][96] */
+int greb_b200_get_fluxcorr(greb_b200_t h, int member, int which, float* out);
+/* last completed year's monthly means of one member: out[12][5][48][96] */
+int greb_b200_get_monthly(greb_b200_t h, int member, float* out);
+/* device-resident per-member diagnostics of the last completed year, 2 floats per member
+ * {unweighted mean, cos-lat mean} in deg C — the vector a multi-GPU driver all-reduces. */
+int greb_b200_diag_device(greb_b200_t h, const float** dev_ptr, int* n_floats);
+/* per-member non-finite flags (1 = a non-finite value was seen) */
+int greb_b200_get_flags(greb_b200_t h, int* flags /*[n_members]*/);
+
+/* ---- kernel-level entries (parity tests against the reference subroutines) ------------------ */
+
+/* circulation(X_in, dX_crcl, h_scl, wz) (src/greb.f90:528-553) for `n` independent fields, using
+ * member `member`'s geometry (pi, kappa) and the wind climatology of step `ityr` (1..730). */
+int greb_b200_circulation(greb_b200_t h, int member, int ityr, const float* X_in, const float* wz, float* dX_crcl,
+                          int n);
+
+/* ---- timing of the last spinup/run call (CUDA events on the launch stream, ms) -------------- */
+int greb_b200_last_kernel_ms(greb_b200_t h, float* ms, int* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GREB_B200_H */

@@ -234,7 +234,7 @@ def main():
         """NCCL all-reduce of ensemble sum / sum of squares of the annual global-mean Tsurf."""
         ptr, n = ens.diag_device()
         class _A:  # __cuda_array_interface__ view of the library's device buffer (no copy)
-            __cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, True), "version": 2}
+            __cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
         d = torch.as_tensor(_A(), device=f"cuda:{local}").view(-1, 2).double()
         s = torch.stack([d.sum(0), (d * d).sum(0)]).flatten()
         if world > 1:

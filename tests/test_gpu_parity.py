@@ -151,10 +151,11 @@ def test_spinup_and_scenario_vs_oracle(oracle_mod, forcing):
     for n in NAMES:
         a, b = o.get(n), ens.get_state(0, n)
         assert np.abs(a.astype(np.float64) - b).max() <= (1e-3 if n != "cap_surf" else 1e-5 * np.abs(a).max()), n
-    scale = [1.0, 1e-4, 1.0]
-    for w in range(3):  # TF [W/m2], qF, ToF
+    # TF = T_error*cap_surf/dt [W/m2]: 1e-4 K of T_error on a deep mixed layer (cap ~8e8) is ~2 W/m2
+    tol = [2.0, 1e-6, 1e-3]
+    for w in range(3):  # TF [W/m2], qF [kg/kg], ToF [K]
         a, b = o.fluxcorr(w), ens.get_fluxcorr(0, w)
-        assert np.abs(a.astype(np.float64) - b).max() <= 0.05 * scale[w], (w, np.abs(a - b).max())
+        assert np.abs(a.astype(np.float64) - b).max() <= tol[w], (w, np.abs(a - b).max())
     out_o, gm_o = o.run(2, co2_ppm=co2)
     ens.reset_scenario()
     out_g, gm_g, gc_g = ens.run(2)

@@ -20,12 +20,15 @@
 //                                            kernels
 // ------------------------------------------------------------------------------------------------
 
-#define GREB_SMEM_BYTES (4 * GNC * (int)sizeof(float))
+#define GREB_SMEM_BYTES (GSM_FLOATS * (int)sizeof(float))
 
-__device__ __forceinline__ void load_member_const(GrebMemberConst* dst, const GrebMemberConst* src) {
+__device__ __forceinline__ void cta_prologue(GrebMemberConst* dst, const GrebMemberConst* src, float* smem) {
   const int* s = reinterpret_cast<const int*>(src);
   int* d = reinterpret_cast<int*>(dst);
   for (int i = threadIdx.x; i < (int)(sizeof(GrebMemberConst) / sizeof(int)); i += blockDim.x) d[i] = s[i];
+  if (threadIdx.x == 0) {
+    sb_init(reinterpret_cast<SplitBar*>(smem + GSM_SYNC), GREB_NWARP);  // one arrival per warp
+  }
   __syncthreads();
 }
 
@@ -35,7 +38,7 @@ __global__ void __launch_bounds__(GREB_NTHREADS, 1) greb_member_kernel(const Gre
   extern __shared__ __align__(16) float smem[];
   __shared__ GrebMemberConst mc_s;
   const int member = a.member_ids[blockIdx.x];
-  load_member_const(&mc_s, a.mc + member);
+  cta_prologue(&mc_s, a.mc + member, smem);
   SimtCtx ctx;
   ctx.warp = warp_uniform(threadIdx.x >> 5);
   ctx.lane_u = threadIdx.x & 31;
@@ -47,27 +50,38 @@ __global__ void __launch_bounds__(GREB_NTHREADS, 1) greb_member_kernel(const Gre
 __global__ void __launch_bounds__(GREB_NTHREADS, 1) greb_circulation_kernel(const GrebCirculationArgs a) {
   extern __shared__ __align__(16) float smem[];
   __shared__ GrebMemberConst mc_s;
-  load_member_const(&mc_s, a.mc);
+  cta_prologue(&mc_s, a.mc, smem);
   SimtCtx ctx;
   ctx.warp = warp_uniform(threadIdx.x >> 5);
   ctx.lane_u = threadIdx.x & 31;
   ctx.smem = smem;
+  SyncState ss;
+  ss.bar = reinterpret_cast<SplitBar*>(smem + GSM_SYNC);
+  ss.hb = smem + GSM_HB;
+  ss.smem = smem;
+  ss.phase = 0;
   const size_t off = (size_t)blockIdx.x * GNC;
-  const WarpGeom g = warp_geom(ctx, mc_s);
-  CircTile t;
-  circ_load_uv(t, g, a.uv, a.uv + GNC);
-  circ_load_wz(t, g, a.wz + off);
-  circ_load_field(t, g, a.X_in + off);
-  circulation_run(ctx, t, g, mc_s, smem);
+  if (!ctx_is_helper(ctx)) {
+    const RowGeom g = row_geom(ctx, mc_s);
+    Tile t;
+    tile_load_uv(t, g, a.uv, a.uv + GNC, smem);
+    tile_load_wz(t, g, a.wz + off, smem);
+    tile_load_field(t, g, a.X_in + off);
+    circulation_main(ctx, t, g, mc_s, ss);
 #pragma unroll
-  for (int r = 0; r < GREB_MAXR; ++r)
-    if (r < g.nr) {
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const int idx = (g.k0 + r) * GX + g.col + c;
-        a.dX[off + idx] = t.Y[r + 2][c] - a.X_in[off + idx];  // f:551
-      }
+    for (int q = 0; q < 3; ++q) {
+      const int idx = g.k * GX + g.col + 4 * q;
+      const float4 x = *reinterpret_cast<const float4*>(a.X_in + off + idx);
+      *reinterpret_cast<float4*>(a.dX + off + idx) = make_float4(t.T[4 * q] - x.x, t.T[4 * q + 1] - x.y,
+                                                                 t.T[4 * q + 2] - x.z, t.T[4 * q + 3] - x.w);  // f:551
     }
+  } else {
+    const HelperGeom hg = helper_geom(ctx, mc_s);
+    HelperRow hr[GREB_HROWS];
+    helper_load_uv(hr, hg, a.uv, a.uv + GNC);
+    helper_load_wz(hr, hg, a.wz + off);
+    circulation_helper(ctx, hr, hg, mc_s, a.X_in + off, ss);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -277,7 +291,16 @@ extern "C" int greb_b200_init(greb_b200_t h) {
   for (int g = 0; g < G; ++g) greb_build_wz(&wz[(size_t)g * 2 * GNC], h->F, h->phys[h->group_rep[g]]);
   for (int m = 0; m < N; ++m) {
     if (m == h->group_rep[h->group_of[m]]) {
-      greb_build_member_const(mc[m], h->phys[m], h->group_of[m]);
+      const int rc = greb_build_member_const(mc[m], h->phys[m], h->group_of[m]);
+      if (rc != 0) {
+        char buf[256];
+        snprintf(buf, sizeof buf,
+                 "greb_b200_init: member %d: kappa = %g / pi = %g need %s, which this kernel does not support", m,
+                 h->phys[m].kappa, h->phys[m].pi,
+                 rc == -1 ? "more than 2 latitude rows besides the poles with several polar diffusion sub-steps"
+                          : "sub-stepped polar advection or a non-polar pole row");
+        return fail(h, GREB_E_INVALID, buf);
+      }
       greb_build_initial_state(&state[(size_t)m * GS_COUNT * GNC], h->F, mc[m]);
     } else {
       const int r = h->group_rep[h->group_of[m]];

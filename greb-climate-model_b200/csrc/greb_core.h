@@ -1,19 +1,25 @@
 // greb_core.h — warp-level implementation of the GREB 12-hourly step for one ensemble member.
 //
-// One CTA (12 warps) integrates one member.  Warp w owns latitude rows [row0, row0+nrow) of the
-// 96x48 grid; a lane owns 3 consecutive longitudes of each of those rows, so a row is exactly one
-// warp wide and the periodic longitude wrap is a lane rotation (SHFL), while the poles are just
-// the first / last rows with their one-sided formulas.  During the 24 circulation sub-steps the
-// advected field, its weights wz and the winds stay in registers; only the two rows next to a
-// warp's band are exchanged through a double-buffered shared-memory copy of the field, with one
-// CTA barrier per sub-step.  Everything else of the step is column-local.
+// One CTA integrates one member.  Thread mapping ("v2"):
+//   * 12 main warps.  A lane group of 8 lanes owns one latitude row; each lane owns 12 consecutive
+//     longitudes of it, so every thread runs the SAME straight-line code on a 12-cell register tile
+//     (the hot loop is ~10 KB of SASS instead of an unrolled per-row body per warp).  The periodic
+//     longitude wrap is a rotation inside the 8-lane group (SHFL); the rows above and below come from
+//     a double-buffered shared-memory copy of the field (LDS.128), published once per sub-step.
+//   * 2 helper warps own the circulation of the two pole rows and of any other row whose polar
+//     x-diffusion needs several sub-sub-steps (time2_diff > 1: 8 dependent iterations on the pole
+//     rows at the default kappa): a whole row per warp at 3 cells per lane, so that serial chain
+//     runs inside one warp, in parallel with the other 46 rows, instead of stalling a main warp.
+//   * the per-sub-step CTA barrier is split-phase (mbarrier): a thread publishes its row, arrives,
+//     does the whole x-direction part of the next sub-step (which needs only its own row), and only
+//     then waits for the neighbours' rows.
 //
 // Arithmetic contract ("exact mode"): the reference is gfortran -O3 without -ffast-math, i.e.
 // IEEE fp32, no FMA contraction, expression order as written.  This file is compiled with
 // -fmad=false; v_fma is used only where it is provably identical to the written form
 // (multiplication by 4 is exact), and the divisions by the literals 3. and 20. use a
-// correctly-rounded 3-instruction sequence (div_c).  Identities used to share work between
-// cells — x-(y) == x+(-y), (-a)*b == -(a*b), RN(-x) == -RN(x), a+b == b+a — are exact in IEEE
+// correctly-rounded 3-instruction sequence.  Identities used to share work between cells —
+// x-(y) == x+(-y), (-a)*b == -(a*b), RN(-x) == -RN(x), a+b == b+a, x+0 == x — are exact in IEEE
 // arithmetic, so results are bit-identical to the as-written evaluation (signs of zeros aside).
 //
 // Reference: /root/reference/src/greb.f90 ("f:NNN" below).
@@ -26,7 +32,8 @@
 
 // ---- correctly rounded x/3 and x/20 ---------------------------------------------------------
 // q0 = x*RN(1/d); r = fma(-d,q0,x); q = fma(r,RN(1/d),q0) equals RN(x/d) for every float x whose
-// quotient is a normal number (exhaustively verified for d = 3 and d = 20 in tests/test_divc.py).
+// quotient is a normal number (verified exhaustively over all 2^32 inputs, tests/test_divc.py and
+// tools/divc_exhaustive.c).
 #if GREB_DEVICE
 GDEV vf div3(vf x) {
   const float r = 0.3333333432674407958984375f;
@@ -48,29 +55,294 @@ GDEV vf div20(vf x) { return x / 20.0f; }
 // clamp of the polar sub-sub-steps: where(d <= -T) d = -0.9*T   (f:715, f:907)
 GDEV vf polar_clamp(vf d, vf T) { return v_sel(d <= -T, -0.9f * T, d); }
 
+// =============================================================================================
+//                    main warps: one 12-cell tile of one latitude row per thread
+// =============================================================================================
+
+struct RowGeom {
+  int k;           // latitude row (uniform within the 8-lane group)
+  int polar;       // f:592 / f:799 branch
+  int ykind;       // 0 interior, 1: k==0, 2: k==1, 3: k==GY-2, 4: k==GY-1   (f:756-795, f:587-590)
+  int owned;       // 0 if the circulation of this row runs on a helper warp (the group then only does the column phases)
+  int km2, km1, kp1, kp2;  // neighbour rows clamped into the grid (absent rows get zero weights)
+  vi col;          // first owned longitude: 12 * (lane & 7)
+  vi lane_l, lane_r;  // SHFL sources: the lanes owning the 12 cells to the west / east
+  vb is_bug;       // the lane group member that owns longitude 93 (its cell 9), see f:881
+  vi tid4;         // 4 * (index of this thread among the 384 main threads): private shared-memory slot
+};
+
+#if GREB_DEVICE
+GDEV bool ctx_is_helper(const SimtCtx& c) { return c.warp >= GREB_NMAIN; }
+GDEV int ctx_helper_index(const SimtCtx& c) { return c.warp - GREB_NMAIN; }
+GDEV int ctx_group(const SimtCtx& c) { return c.warp * 4 + (c.lane_u >> 3); }
+GDEV RowGeom row_geom(const SimtCtx& c, const GrebMemberConst& mc) {
+  RowGeom g;
+  const int seg = c.lane_u & 7, base = c.lane_u & 24;
+  g.k = mc.row_of_group[ctx_group(c)];
+  g.col = 12 * seg;
+  g.lane_l = base | ((seg + 7) & 7);
+  g.lane_r = base | ((seg + 1) & 7);
+  g.is_bug = (seg == 7);
+  g.tid4 = 4 * (c.warp * 32 + c.lane_u);
+#else
+GDEV bool ctx_is_helper(const SimtCtx& c) { return c.warp >= GY; }       // emu: unit index
+GDEV int ctx_helper_index(const SimtCtx& c) { return c.warp - GY; }
+GDEV int ctx_group(const SimtCtx& c) { return c.warp; }
+GDEV RowGeom row_geom(const SimtCtx& c, const GrebMemberConst& mc) {
+  RowGeom g;
+  const vi seg = ctx_lane(c) & 7;   // emu: lanes 0..7 of the vector are the group, the rest is unused
+  g.k = mc.row_of_group[ctx_group(c)];
+  g.col = seg * 12;
+  g.lane_l = (seg + 7) & 7;
+  g.lane_r = (seg + 1) & 7;
+  g.is_bug = (seg == 7);
+  g.tid4 = (seg + 8 * ctx_group(c)) * 4;
+#endif
+  g.polar = mc.polar[g.k];
+  g.ykind = g.k == 0 ? 1 : g.k == 1 ? 2 : g.k == GY - 2 ? 3 : g.k == GY - 1 ? 4 : 0;
+  g.owned = mc.hslot_of_row[g.k] < 0;
+  g.km2 = g.k >= 2 ? g.k - 2 : 0;
+  g.km1 = g.k >= 1 ? g.k - 1 : 0;
+  g.kp1 = g.k <= GY - 2 ? g.k + 1 : GY - 1;
+  g.kp2 = g.k <= GY - 3 ? g.k + 2 : GY - 1;
+  return g;
+}
+
+struct Tile {
+  vf T[GREB_CPT];        // the circulating field, own cells
+  vf W[GREB_CPT];        // wz, own cells
+  vf U[GREB_CPT];        // zonal wind of this step
+  vf wxl[3], wxr[3];     // wz of the 3 cells west / east of the tile
+  // The y-direction constants live in a private shared-memory slot of the thread (GSM_PRIV), not in
+  // registers: V, wz(k-1), wz(k+1) (0 where the row does not exist) and the upstream far-row weight
+  // WFY = v>=0 ? wz(k-2) : wz(k+2) (0 if absent).  They are read back with LDS.128 in substep_y.
+};
+
+GDEV float* priv_ptr(float* smem, int which, int q) { return smem + GSM_PRIV + (which * 3 + q) * (GREB_NMAIN * 32 * 4); }
+
+GDEV void tile_load_uv(Tile& t, const RowGeom& g, const float* u, const float* v, float* smem) {
+  GUNROLL
+  for (int q = 0; q < 3; ++q) {
+    vf a[4], b[4];
+    v_ldg4(a, u, g.k * GX + g.col + 4 * q);
+    v_ldg4(b, v, g.k * GX + g.col + 4 * q);
+    GUNROLL
+    for (int i = 0; i < 4; ++i) t.U[4 * q + i] = a[i];
+    v_st4(priv_ptr(smem, PRIV_V, q), g.tid4, b[0], b[1], b[2], b[3]);
+  }
+}
+
+// wz-dependent constants of one circulation (needs V of tile_load_uv)
+GDEV void tile_load_wz(Tile& t, const RowGeom& g, const float* wz, float* smem) {
+  const bool has_m1 = g.k >= 1, has_m2 = g.k >= 2, has_p1 = g.k <= GY - 2, has_p2 = g.k <= GY - 3;
+  GUNROLL
+  for (int q = 0; q < 3; ++q) {
+    vf w0[4], wm1[4], wp1[4], wm2[4], wp2[4], v[4], wfy[4];
+    v_ldg4(w0, wz, g.k * GX + g.col + 4 * q);
+    v_ldg4(wm1, wz, g.km1 * GX + g.col + 4 * q);
+    v_ldg4(wp1, wz, g.kp1 * GX + g.col + 4 * q);
+    v_ldg4(wm2, wz, g.km2 * GX + g.col + 4 * q);
+    v_ldg4(wp2, wz, g.kp2 * GX + g.col + 4 * q);
+    v_ld4(v, priv_ptr(smem, PRIV_V, q), g.tid4);
+    GUNROLL
+    for (int i = 0; i < 4; ++i) {
+      t.W[4 * q + i] = w0[i];
+      if (!has_m1) wm1[i] = v_bcast(0.0f);
+      if (!has_p1) wp1[i] = v_bcast(0.0f);
+      const vf a = has_m2 ? wm2[i] : v_bcast(0.0f);
+      const vf b = has_p2 ? wp2[i] : v_bcast(0.0f);
+      wfy[i] = v_sel(v[i] >= 0.0f, a, b);
+    }
+    v_st4(priv_ptr(smem, PRIV_WM1, q), g.tid4, wm1[0], wm1[1], wm1[2], wm1[3]);
+    v_st4(priv_ptr(smem, PRIV_WP1, q), g.tid4, wp1[0], wp1[1], wp1[2], wp1[3]);
+    v_st4(priv_ptr(smem, PRIV_WFY, q), g.tid4, wfy[0], wfy[1], wfy[2], wfy[3]);
+  }
+  GUNROLL
+  for (int i = 0; i < 3; ++i) {
+    // periodic wrap of the longitude index
+    const vi cl = v_seli(g.col == 0, vi(GX - 3 + i), g.col - 3 + i);
+    const vi cr = v_seli(g.col == GX - 12, vi(i), g.col + 12 + i);
+    t.wxl[i] = v_ldg(wz, g.k * GX + cl);
+    t.wxr[i] = v_ldg(wz, g.k * GX + cr);
+  }
+}
+
+GDEV void tile_load_field(Tile& t, const RowGeom& g, const float* X) {
+  GUNROLL
+  for (int q = 0; q < 3; ++q) {
+    vf a[4];
+    v_ld4(a, X, g.k * GX + g.col + 4 * q);
+    GUNROLL
+    for (int i = 0; i < 4; ++i) t.T[4 * q + i] = a[i];
+  }
+}
+
+GDEV void tile_publish(const Tile& t, const RowGeom& g, float* buf) {
+  GUNROLL
+  for (int q = 0; q < 3; ++q)
+    v_st4(buf, g.k * GX + g.col + 4 * q, t.T[4 * q], t.T[4 * q + 1], t.T[4 * q + 2], t.T[4 * q + 3]);
+}
+
 // ---------------------------------------------------------------------------------------------
-// x-direction products of one row segment (3 own cells + neighbours).
-//   d(m) = T(m+1)-T(m),  P(m) = wz(m)*d(m),  Q(m) = wz(m+1)*d(m)
-// With c0 the lane's first cell: Pm3..P1 = P(c0-3..c0+1), Q0..Qp2 = Q(c0..c0+4).
+// x-direction part of one sub-step (needs only the thread's own row):
+//   dTx = longitudinal diffusion increment (f:592-719), aTx = longitudinal advection (f:798-911)
+// Notation: d(m) = T(m+1)-T(m),  P(m) = wz(m)*d(m),  Q(m) = wz(m+1)*d(m); arrays are indexed
+// e = m + 3 where m is the cell index relative to the tile (m = -3 .. 14).
 // ---------------------------------------------------------------------------------------------
+GDEV void substep_x(vf (&dTx)[GREB_CPT], vf (&aTx)[GREB_CPT], const Tile& t, const RowGeom& g,
+                    const GrebMemberConst& mc) {
+  vf TT[18], WW[18];
+  GUNROLL
+  for (int i = 0; i < 3; ++i) {
+    TT[i] = v_shfl(t.T[9 + i], g.lane_l);
+    TT[15 + i] = v_shfl(t.T[i], g.lane_r);
+    WW[i] = t.wxl[i];
+    WW[15 + i] = t.wxr[i];
+  }
+  GUNROLL
+  for (int i = 0; i < GREB_CPT; ++i) {
+    TT[3 + i] = t.T[i];
+    WW[3 + i] = t.W[i];
+  }
+  vf d[17], P[17], Q[17], A[17], B[17], S[GREB_CPT];
+  GUNROLL
+  for (int e = 0; e < 17; ++e) d[e] = TT[e + 1] - TT[e];
+  GUNROLL
+  for (int e = 0; e <= 13; ++e) P[e] = WW[e] * d[e];
+  GUNROLL
+  for (int e = 3; e <= 16; ++e) Q[e] = WW[e + 1] * d[e];
+  GUNROLL
+  for (int e = 1; e <= 13; ++e) A[e] = P[e] - P[e - 1];  // A(m) = P(m)-P(m-1)
+  GUNROLL
+  for (int e = 3; e <= 15; ++e) B[e] = Q[e + 1] - Q[e];  // B(m) = Q(m+1)-Q(m)
+  // bracket of f:620-625: 10*(Q(j)-P(j-1)) + 4*A(j-1) + 4*B(j) + A(j-2) + B(j+1)
+  GUNROLL
+  for (int j = 0; j < GREB_CPT; ++j) {
+    const int e = j + 3;
+    const vf G = Q[e] - P[e - 1];
+    S[j] = v_fma(4.0f, B[e], v_fma(4.0f, A[e - 1], 10.0f * G)) + A[e - 2] + B[e + 1];
+  }
+  if (!g.polar) {
+    const float cc = mc.ccx_diff[g.k], cca = mc.ccx_adv[g.k];
+    GUNROLL
+    for (int j = 0; j < GREB_CPT; ++j) {
+      const int e = j + 3;
+      dTx[j] = div20(cc * S[j]);
+      // f:816-820: -um*(wz(j-1)*(T-T(j-1)) + wz(j-2)*(T-T(j-2))) + up*(wz(j+1)*(T-T(j+1)) + wz(j+2)*(T-T(j+2)))
+      // exactly one of um, up is non-zero: select the upstream side, multiply by -|u|
+      const vb pu = t.U[j] >= 0.0f;
+      const vf near = v_sel(pu, P[e - 1], -Q[e]);
+      const vf far = v_sel(pu, WW[e - 2], WW[e + 2]) * (TT[e] - v_sel(pu, TT[e - 2], TT[e + 2]));
+      const vf Xu = (-v_abs(t.U[j])) * (near + far);
+      aTx[j] = div3(cca * Xu);
+    }
+  } else {
+    const float cc2 = mc.ccx2_diff[g.k], cca2 = mc.ccx2_adv[g.k];
+    GUNROLL
+    for (int j = 0; j < GREB_CPT; ++j) {
+      const int e = j + 3;
+      {  // f:659-718 with time2 == 1 (rows with more sub-sub-steps are overwritten from the helper)
+        vf dd = div20(cc2 * S[j]);
+        dd = polar_clamp(dd, t.T[j]);
+        const vf h = t.T[j] + dd;
+        dTx[j] = h - t.T[j];
+      }
+      // f:872-878: -um*(10*wz(j-1)*(T(j)-T(j-1)) + 4*wz(j-2)*(T(j-1)-T(j-2)) + wz(j-3)*(T(j-2)-T(j-3)))
+      //            + up*(10*wz(j+1)*(T(j)-T(j+1)) + 4*wz(j+2)*(T(j+1)-T(j+2)) + wz(j+3)*(T(j+2)-T(j+3)))
+      const vb pu = t.U[j] >= 0.0f;
+      const vf near10 = (10.0f * v_sel(pu, WW[e - 1], WW[e + 1])) * v_sel(pu, d[e - 1], d[e]);
+      vf mid = v_sel(pu, P[e - 2], Q[e + 1]);
+      vf far = v_sel(pu, P[e - 3], Q[e + 2]);
+      if (j == 9) {
+        // f:881: at Fortran j = xdim-2 (0-based longitude 93 = cell 9 of the last lane of the group)
+        // the reference sets jp1 = jp2 = xdim-1, jp3 = 1: the 4* term vanishes and the 1* term is
+        // wz(1)*(T(xdim-1)-T(1)).  Reproduced verbatim.
+        const vb bug = g.is_bug && !pu;
+        mid = v_sel(bug, v_bcast(0.0f), mid);
+        far = v_sel(bug, WW[15] * (TT[15] - TT[13]), far);
+      }
+      const vf Sa = v_fma(4.0f, mid, near10) + far;
+      const vf Xu = (-t.U[j]) * Sa;
+      vf dd = div20(cca2 * Xu);
+      dd = polar_clamp(dd, t.T[j]);  // f:907
+      const vf h = t.T[j] + dd;      // f:908
+      aTx[j] = h - t.T[j];           // f:910
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// y-direction part + update: needs rows k-2..k+2 of the published field `buf`.
+//   out = (T + wz*(dTx+dTy)) + (aTx+aTy)                                  (f:721, f:913, f:549)
+// SPECIAL = the thread's row is row 2 or row ydim-1 (1-based), whose advection divides only one of
+// the two wind branches by 3 (f:766-769, f:784-787).  Rows 1 and ydim are always helper-owned.
+// ---------------------------------------------------------------------------------------------
+template <bool SPECIAL>
+GDEV void substep_y(Tile& t, const vf (&dTx)[GREB_CPT], const vf (&aTx)[GREB_CPT], const RowGeom& g,
+                    const GrebMemberConst& mc, const float* buf, float* smem) {
+  const float ccyd = mc.ccy_diff, ccya = mc.ccy_adv;
+  GUNROLL
+  for (int q = 0; q < 3; ++q) {
+    vf tm2[4], tm1[4], tp1[4], tp2[4], V[4], Wm1[4], Wp1[4], WFY[4];
+    v_ld4(V, priv_ptr(smem, PRIV_V, q), g.tid4);
+    v_ld4(Wm1, priv_ptr(smem, PRIV_WM1, q), g.tid4);
+    v_ld4(Wp1, priv_ptr(smem, PRIV_WP1, q), g.tid4);
+    v_ld4(WFY, priv_ptr(smem, PRIV_WFY, q), g.tid4);
+    v_ld4(tm1, buf, g.km1 * GX + g.col + 4 * q);
+    v_ld4(tp1, buf, g.kp1 * GX + g.col + 4 * q);
+    v_ld4(tm2, buf, g.km2 * GX + g.col + 4 * q);
+    v_ld4(tp2, buf, g.kp2 * GX + g.col + 4 * q);
+    GUNROLL
+    for (int i = 0; i < 4; ++i) {
+      const int j = 4 * q + i;
+      const vf T = t.T[j];
+      const vf Pym1 = Wm1[i] * (T - tm1[i]);    // wz(k-1)*(T(k)-T(k-1))
+      const vf Qy0 = Wp1[i] * (tp1[i] - T);     // wz(k+1)*(T(k+1)-T(k))
+      // diffusion, latitudinal (f:587-588)
+      const vf dTy = ccyd * (Qy0 - Pym1);
+      // advection, latitudinal (f:771-780): upstream side selected by the sign of v
+      const vb pv = V[i] >= 0.0f;
+      const vf near = v_sel(pv, Pym1, -Qy0);
+      const vf far = WFY[i] * (T - v_sel(pv, tm2[i], tp2[i]));
+      const vf Xv = (-v_abs(V[i])) * (near + far);
+      vf aTy;
+      if (!SPECIAL) {
+        aTy = div3(ccya * Xv);
+      } else {
+        // row 2: v>=0 branch is not divided at all, v<0 branch is divided before the ccy multiply;
+        // row ydim-1: the other way round
+        const vb plain = (g.ykind == 2) ? pv : !pv;
+        aTy = v_sel(plain, ccya * Xv, ccya * div3(Xv));
+      }
+      const vf dXd = t.W[j] * (dTx[j] + dTy);   // f:721
+      const vf dXa = aTx[j] + aTy;              // f:913
+      t.T[j] = (T + dXd) + dXa;                 // f:549
+    }
+  }
+}
+
+// =============================================================================================
+//   helper warps: whole latitude rows at 3 cells per lane (the pole rows and every row whose polar
+//   x-diffusion needs several sub-sub-steps).  Only polar-branch rows are ever helper-owned.
+// =============================================================================================
 struct XRow {
-  vf xm2, xm1, xp1, xp2;            // T(c0-2), T(c0-1), T(c0+3), T(c0+4)
-  vf dm1, d0, d1, d2;               // d(c0-1..c0+2)
+  vf xm1, xp1;                 // T(c0-1), T(c0+3)
+  vf dm1, d0, d1, d2;          // d(c0-1..c0+2)
   vf Pm3, Pm2, Pm1, P0, P1;
   vf Q0, Q1, Q2, Qp1, Qp2;
 };
 
+// With c0 the lane's first cell: Pm3..P1 = P(c0-3..c0+1), Q0..Qp2 = Q(c0..c0+4).
 GDEV void xrow_products(XRow& x, const vf (&T)[3], const vf (&W)[3], const vf (&WX)[4], vi lane_l, vi lane_r) {
-  x.xm2 = v_shfl(T[1], lane_l);
+  const vf xm2 = v_shfl(T[1], lane_l);
   x.xm1 = v_shfl(T[2], lane_l);
   x.xp1 = v_shfl(T[0], lane_r);
-  x.xp2 = v_shfl(T[1], lane_r);
-  const vf dm2 = x.xm1 - x.xm2;
+  const vf xp2 = v_shfl(T[1], lane_r);
+  const vf dm2 = x.xm1 - xm2, dp1 = xp2 - x.xp1;
   x.dm1 = T[0] - x.xm1;
   x.d0 = T[1] - T[0];
   x.d1 = T[2] - T[1];
   x.d2 = x.xp1 - T[2];
-  const vf dp1 = x.xp2 - x.xp1;
   x.Pm2 = WX[0] * dm2;
   x.Pm1 = WX[1] * x.dm1;
   x.P0 = W[0] * x.d0;
@@ -79,373 +351,262 @@ GDEV void xrow_products(XRow& x, const vf (&T)[3], const vf (&W)[3], const vf (&
   x.Q1 = W[2] * x.d1;
   x.Q2 = WX[2] * x.d2;
   x.Qp1 = WX[3] * dp1;
-  x.Pm3 = v_shfl(x.P0, lane_l);   // left lane's P(c0') = P(c0-3)
-  x.Qp2 = v_shfl(x.Q1, lane_r);   // right lane's Q(c0'+1) = Q(c0+4)
+  x.Pm3 = v_shfl(x.P0, lane_l);  // left lane's P(c0') = P(c0-3)
+  x.Qp2 = v_shfl(x.Q1, lane_r);  // right lane's Q(c0'+1) = Q(c0+4)
 }
 
-// the bracket of f:620-625 for the 3 own cells:
-//   10*(Q(j)-P(j-1)) + 4*(P(j-1)-P(j-2)) + 4*(Q(j+1)-Q(j)) + (P(j-2)-P(j-3)) + (Q(j+2)-Q(j+1))
-GDEV void xdiff_bracket(vf (&S)[3], const XRow& x) {
-  const vf Am2 = x.Pm2 - x.Pm3, Am1 = x.Pm1 - x.Pm2, A0 = x.P0 - x.Pm1, A1 = x.P1 - x.P0;  // A(m)=P(m)-P(m-1)
-  const vf B0 = x.Q1 - x.Q0, B1 = x.Q2 - x.Q1, B2 = x.Qp1 - x.Q2, B3 = x.Qp2 - x.Qp1;     // B(m)=Q(m+1)-Q(m)
+GDEV void xdiff_bracket3(vf (&S)[3], const XRow& x) {
+  const vf Am2 = x.Pm2 - x.Pm3, Am1 = x.Pm1 - x.Pm2, A0 = x.P0 - x.Pm1, A1 = x.P1 - x.P0;
+  const vf B0 = x.Q1 - x.Q0, B1 = x.Q2 - x.Q1, B2 = x.Qp1 - x.Q2, B3 = x.Qp2 - x.Qp1;
   const vf G0 = x.Q0 - x.Pm1, G1 = x.Q1 - x.P0, G2 = x.Q2 - x.P1;
   S[0] = v_fma(4.0f, B0, v_fma(4.0f, Am1, 10.0f * G0)) + Am2 + B1;
   S[1] = v_fma(4.0f, B1, v_fma(4.0f, A0, 10.0f * G1)) + Am1 + B2;
   S[2] = v_fma(4.0f, B2, v_fma(4.0f, A1, 10.0f * G2)) + A0 + B3;
 }
 
-// one extra polar diffusion sub-sub-step on the row copy h (f:656-717), generic slow path
-GDEV void xdiff_polar_iter(vf (&h)[3], const vf (&W)[3], const vf (&WX)[4], vi lane_l, vi lane_r, float ccx2) {
-  XRow x;
-  xrow_products(x, h, W, WX, lane_l, lane_r);
-  vf S[3];
-  xdiff_bracket(S, x);
-  GUNROLL
-  for (int c = 0; c < 3; ++c) {
-    vf d = div20(ccx2 * S[c]);
-    d = polar_clamp(d, h[c]);
-    h[c] = h[c] + d;
-  }
-}
+#define GREB_HROWS (GREB_MAXH / GREB_NHELP)  // rows per helper warp
 
-// polar x-advection bracket (f:872-878 and the wrap cases incl. the index bug of f:881) for the
-// 3 own cells of a row copy h; returns X = -um*(...) + up*(...) per cell.
-GDEV void xadv_polar_X(vf (&X)[3], const XRow& x, const vf (&T)[3], const vf (&W)[3], const vf (&WX)[4],
-                       const vf (&U)[3], vb is_bug_lane) {
-  // per own cell: P(j-1), P(j-2), P(j-3) / Q(j), Q(j+1), Q(j+2), d(j-1) / d(j), wz(j-1) / wz(j+1)
-  const vf dlo[3] = {x.dm1, x.d0, x.d1}, dhi[3] = {x.d0, x.d1, x.d2};
-  const vf wlo[3] = {WX[1], W[0], W[1]}, whi[3] = {W[1], W[2], WX[2]};
-  const vf P2[3] = {x.Pm2, x.Pm1, x.P0}, P3[3] = {x.Pm3, x.Pm2, x.Pm1};
-  const vf Qn1[3] = {x.Q1, x.Q2, x.Qp1}, Qn2[3] = {x.Q2, x.Qp1, x.Qp2};
-  GUNROLL
-  for (int c = 0; c < 3; ++c) {
-    const vb pu = U[c] >= 0.0f;
-    const vf near10 = (10.0f * v_sel(pu, wlo[c], whi[c])) * v_sel(pu, dlo[c], dhi[c]);
-    vf mid = v_sel(pu, P2[c], Qn1[c]);
-    vf far = v_sel(pu, P3[c], Qn2[c]);
-    if (c == 0) {
-      // f:881: Fortran j = xdim-2 (0-based 93 = lane 31, cell 0) uses jp1 = jp2 = xdim-1, jp3 = 1:
-      // the 4* term vanishes and the 1* term is wz(1)*(T(xdim-1)-T(1)).
-      const vb bug = is_bug_lane && !pu;
-      mid = v_sel(bug, v_bcast(0.0f), mid);
-      far = v_sel(bug, WX[2] * (x.xp1 - T[1]), far);
-    }
-    const vf S = v_fma(4.0f, mid, near10) + far;
-    X[c] = (-U[c]) * S;
-  }
-}
-
-GDEV void xadv_polar_iter(vf (&h)[3], const vf (&W)[3], const vf (&WX)[4], const vf (&U)[3], vi lane_l,
-                          vi lane_r, vb is_bug_lane, float ccx2) {
-  XRow x;
-  xrow_products(x, h, W, WX, lane_l, lane_r);
-  vf X[3];
-  xadv_polar_X(X, x, h, W, WX, U, is_bug_lane);
-  GUNROLL
-  for (int c = 0; c < 3; ++c) {
-    vf d = div20(ccx2 * X[c]);
-    d = polar_clamp(d, h[c]);
-    h[c] = h[c] + d;
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// One circulation sub-step for the 3 cells a lane owns in latitude row k:
-//   out = (T + dX_diffuse) + dX_advec                                    (f:547-549)
-// Tm2..Tp2 / Wm2..Wp2 are the rows k-2..k+2 of the field and of wz (values of rows outside
-// 0..47 are never used: the boundary rows have their own formulas).
-// ---------------------------------------------------------------------------------------------
-GDEV void row_update(vf (&out)[3], const GrebMemberConst& mc, int k, const vf (&Tm2)[3], const vf (&Tm1)[3],
-                     const vf (&T)[3], const vf (&Tp1)[3], const vf (&Tp2)[3], const vf (&Wm2)[3],
-                     const vf (&Wm1)[3], const vf (&W)[3], const vf (&Wp1)[3], const vf (&Wp2)[3],
-                     const vf (&WX)[4], const vf (&U)[3], const vf (&V)[3], vi lane_l, vi lane_r,
-                     vb is_bug_lane) {
-  const bool polar = mc.polar[k] != 0;
-  XRow x;
-  xrow_products(x, T, W, WX, lane_l, lane_r);
-
-  // ---------------- diffusion, longitudinal (f:592-719) ----------------
-  vf dTx[3];
-  {
-    vf S[3];
-    xdiff_bracket(S, x);
-    if (!polar) {
-      const float cc = mc.ccx_diff[k];
-      GUNROLL
-      for (int c = 0; c < 3; ++c) dTx[c] = div20(cc * S[c]);
-    } else {
-      const float cc2 = mc.ccx2_diff[k];
-      vf h[3];
-      GUNROLL
-      for (int c = 0; c < 3; ++c) {
-        vf d = div20(cc2 * S[c]);
-        d = polar_clamp(d, T[c]);   // f:715
-        h[c] = T[c] + d;            // f:716
-      }
-      const int time2 = mc.time2_diff[k];
-      GNOUNROLL
-      for (int tt2 = 1; tt2 < time2; ++tt2) xdiff_polar_iter(h, W, WX, lane_l, lane_r, cc2);
-      GUNROLL
-      for (int c = 0; c < 3; ++c) dTx[c] = h[c] - T[c];  // f:718
-    }
-  }
-
-  // ---------------- y-direction edge products ----------------
-  vf Pym1[3], Qy0[3];  // wz(k-1)*(T(k)-T(k-1)),  wz(k+1)*(T(k+1)-T(k))
-  GUNROLL
-  for (int c = 0; c < 3; ++c) {
-    Pym1[c] = Wm1[c] * (T[c] - Tm1[c]);
-    Qy0[c] = Wp1[c] * (Tp1[c] - T[c]);
-  }
-
-  // ---------------- diffusion, latitudinal (f:587-590) ----------------
-  vf dTy[3];
-  {
-    const float ccy = mc.ccy_diff;
-    if (k >= 1 && k <= GY - 2) {
-      GUNROLL
-      for (int c = 0; c < 3; ++c) dTy[c] = ccy * (Qy0[c] - Pym1[c]);
-    } else if (k == 0) {
-      GUNROLL
-      for (int c = 0; c < 3; ++c) dTy[c] = (ccy * Wp1[c]) * (Tp1[c] - T[c]);
-    } else {
-      GUNROLL
-      for (int c = 0; c < 3; ++c) dTy[c] = (ccy * Wm1[c]) * (Tm1[c] - T[c]);
-    }
-  }
-
-  // ---------------- advection, latitudinal (f:756-795) ----------------
-  vf aTy[3];
-  {
-    const float ccy = mc.ccy_adv;
-    if (k >= 2 && k <= GY - 3) {  // f:774-778
-      GUNROLL
-      for (int c = 0; c < 3; ++c) {
-        const vb pv = V[c] >= 0.0f;
-        const vf near = v_sel(pv, Pym1[c], -Qy0[c]);
-        const vf far = v_sel(pv, Wm2[c], Wp2[c]) * (T[c] - v_sel(pv, Tm2[c], Tp2[c]));
-        const vf Xv = (-v_abs(V[c])) * (near + far);
-        aTy[c] = div3(ccy * Xv);
-      }
-    } else {
-      GUNROLL
-      for (int c = 0; c < 3; ++c) {
-        const vb pv = V[c] >= 0.0f;
-        const vf vm = v_sel(pv, V[c], v_bcast(0.0f));   // f:210-216
-        const vf vp = v_sel(pv, v_bcast(0.0f), V[c]);
-        if (k == 0) {  // f:759-761
-          const vf s2 = (-Qy0[c]) + Wp2[c] * (T[c] - Tp2[c]);
-          aTy[c] = div3(ccy * (vp * s2));
-        } else if (k == 1) {  // f:766-769
-          const vf s2 = (-Qy0[c]) + Wp2[c] * (T[c] - Tp2[c]);
-          aTy[c] = ccy * (-(vm * Pym1[c]) + div3(vp * s2));
-        } else if (k == GY - 2) {  // f:784-787
-          const vf s1 = Pym1[c] + Wm2[c] * (T[c] - Tm2[c]);
-          aTy[c] = ccy * (-div3(vm * s1) + vp * (-Qy0[c]));
-        } else {  // k == GY-1, f:792-794
-          const vf s1 = Pym1[c] + Wm2[c] * (T[c] - Tm2[c]);
-          aTy[c] = div3(ccy * (-(vm * s1)));
-        }
-      }
-    }
-  }
-
-  // ---------------- advection, longitudinal (f:798-911) ----------------
-  vf aTx[3];
-  if (!polar) {  // f:816-820 and wrap cases
-    const float cc = mc.ccx_adv[k];
-    const vf nearP[3] = {x.Pm1, x.P0, x.P1}, nearQ[3] = {x.Q0, x.Q1, x.Q2};
-    const vf tfm[3] = {x.xm2, x.xm1, T[0]}, tfp[3] = {T[2], x.xp1, x.xp2};
-    const vf wfm[3] = {WX[0], WX[1], W[0]}, wfp[3] = {W[2], WX[2], WX[3]};
-    GUNROLL
-    for (int c = 0; c < 3; ++c) {
-      const vb pu = U[c] >= 0.0f;
-      const vf near = v_sel(pu, nearP[c], -nearQ[c]);
-      const vf far = v_sel(pu, wfm[c], wfp[c]) * (T[c] - v_sel(pu, tfm[c], tfp[c]));
-      const vf Xu = (-v_abs(U[c])) * (near + far);
-      aTx[c] = div3(cc * Xu);
-    }
-  } else {  // f:838-910
-    const float cc2 = mc.ccx2_adv[k];
-    vf X[3], h[3];
-    xadv_polar_X(X, x, T, W, WX, U, is_bug_lane);
-    GUNROLL
-    for (int c = 0; c < 3; ++c) {
-      vf d = div20(cc2 * X[c]);
-      d = polar_clamp(d, T[c]);  // f:907
-      h[c] = T[c] + d;           // f:908
-    }
-    const int time2 = mc.time2_adv[k];
-    GNOUNROLL
-    for (int tt2 = 1; tt2 < time2; ++tt2) xadv_polar_iter(h, W, WX, U, lane_l, lane_r, is_bug_lane, cc2);
-    GUNROLL
-    for (int c = 0; c < 3; ++c) aTx[c] = h[c] - T[c];  // f:910
-  }
-
-  GUNROLL
-  for (int c = 0; c < 3; ++c) {
-    const vf dXd = W[c] * (dTx[c] + dTy[c]);  // f:721
-    const vf dXa = aTx[c] + aTy[c];           // f:913
-    out[c] = (T[c] + dXd) + dXa;              // f:549
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// Per-warp register tile for the circulation.
-// Row slots: Y[0..1] = rows k0-2, k0-1 (lower halo); Y[2..2+nr) = own rows; then 2 upper halo rows.
-// ---------------------------------------------------------------------------------------------
-struct CircTile {
-  vf Y[GREB_MAXR + 4][3];
-  vf WY[GREB_MAXR + 4][3];
-  vf WX[GREB_MAXR][4];
-  vf U[GREB_MAXR][3], V[GREB_MAXR][3];
+struct HelperRow {
+  vf T[3];                                   // the circulating field
+  vf W[3], WX[4];                            // wz of the own cells and of c0-2, c0-1, c0+3, c0+4
+  vf U[3], V[3];
+  vf Wm1[3], Wp1[3], WFY[3];                 // as in the main tile (0 where the row does not exist)
+  vf dTx[3], aTx[3];                         // x-direction results of the current sub-step
 };
 
-struct WarpGeom {
-  int k0, nr;          // owned rows [k0, k0+nr)
-  vi col;              // 3*lane: first owned longitude
-  vi lane_l, lane_r;   // rotating neighbours
-  vb is_bug_lane;      // lane 31
+struct HelperGeom {
+  int n;                       // rows served by this helper warp
+  int k[GREB_HROWS];
+  vi col, lane_l, lane_r;
+  vb is_bug;                   // lane 31 owns longitude 93 as its first cell (f:881)
 };
 
-GDEV WarpGeom warp_geom(const SimtCtx& ctx, const GrebMemberConst& mc) {
-  WarpGeom g;
-  g.k0 = warp_uniform(mc.row0[ctx.warp]);
-  g.nr = warp_uniform(mc.nrow[ctx.warp]);
+GDEV HelperGeom helper_geom(const SimtCtx& ctx, const GrebMemberConst& mc) {
+  HelperGeom g;
   const vi lane = ctx_lane(ctx);
   g.col = lane * 3;
   g.lane_l = (lane + 31) & 31;
   g.lane_r = (lane + 1) & 31;
-  g.is_bug_lane = (lane == 31);
+  g.is_bug = (lane == 31);
+  g.n = 0;
+  GUNROLL
+  for (int i = 0; i < GREB_HROWS; ++i) {
+    const int s = ctx_helper_index(ctx) + i * GREB_NHELP;
+    g.k[i] = (s < mc.n_hslots) ? mc.helper_row[s] : 0;
+    if (s < mc.n_hslots) g.n = i + 1;
+  }
   return g;
 }
 
-// wz rows (own + halo) and wz x-halos from a [GNC] field in global memory
-GDEV void circ_load_wz(CircTile& t, const WarpGeom& g, const float* wz) {
+GDEV void helper_load_uv(HelperRow (&hr)[GREB_HROWS], const HelperGeom& g, const float* u, const float* v) {
   GUNROLL
-  for (int s = 0; s < GREB_MAXR + 4; ++s) {
-    const int k = g.k0 - 2 + s;
-    const bool ok = (k >= 0) && (k < GY) && (s < g.nr + 4);
+  for (int i = 0; i < GREB_HROWS; ++i)
     GUNROLL
-    for (int c = 0; c < 3; ++c) t.WY[s][c] = ok ? v_ldg(wz, k * GX + g.col + c) : v_bcast(0.0f);
-  }
-  // x-halo columns c0-2, c0-1, c0+3, c0+4 (periodic)
+    for (int c = 0; c < 3; ++c) {
+      hr[i].U[c] = v_ldg(u, g.k[i] * GX + g.col + c);
+      hr[i].V[c] = v_ldg(v, g.k[i] * GX + g.col + c);
+    }
+}
+
+GDEV void helper_load_wz(HelperRow (&hr)[GREB_HROWS], const HelperGeom& g, const float* wz) {
   const vi cm2 = v_seli(g.col == 0, vi(GX - 2), g.col - 2);
   const vi cm1 = v_seli(g.col == 0, vi(GX - 1), g.col - 1);
   const vi cp1 = v_seli(g.col == GX - 3, vi(0), g.col + 3);
   const vi cp2 = v_seli(g.col == GX - 3, vi(1), g.col + 4);
   GUNROLL
-  for (int r = 0; r < GREB_MAXR; ++r) {
-    const bool ok = r < g.nr;
-    const int k = ok ? g.k0 + r : g.k0;
-    t.WX[r][0] = v_ldg(wz, k * GX + cm2);
-    t.WX[r][1] = v_ldg(wz, k * GX + cm1);
-    t.WX[r][2] = v_ldg(wz, k * GX + cp1);
-    t.WX[r][3] = v_ldg(wz, k * GX + cp2);
-  }
-}
-
-GDEV void circ_load_uv(CircTile& t, const WarpGeom& g, const float* u, const float* v) {
-  GUNROLL
-  for (int r = 0; r < GREB_MAXR; ++r) {
-    const int k = (r < g.nr) ? g.k0 + r : g.k0;
+  for (int i = 0; i < GREB_HROWS; ++i) {
+    const int k = g.k[i];
+    const int km1 = k >= 1 ? k - 1 : 0, km2 = k >= 2 ? k - 2 : 0;
+    const int kp1 = k <= GY - 2 ? k + 1 : GY - 1, kp2 = k <= GY - 3 ? k + 2 : GY - 1;
     GUNROLL
     for (int c = 0; c < 3; ++c) {
-      t.U[r][c] = v_ldg(u, k * GX + g.col + c);
-      t.V[r][c] = v_ldg(v, k * GX + g.col + c);
+      hr[i].W[c] = v_ldg(wz, k * GX + g.col + c);
+      hr[i].Wm1[c] = (k >= 1) ? v_ldg(wz, km1 * GX + g.col + c) : v_bcast(0.0f);
+      hr[i].Wp1[c] = (k <= GY - 2) ? v_ldg(wz, kp1 * GX + g.col + c) : v_bcast(0.0f);
+      const vf a = (k >= 2) ? v_ldg(wz, km2 * GX + g.col + c) : v_bcast(0.0f);
+      const vf b = (k <= GY - 3) ? v_ldg(wz, kp2 * GX + g.col + c) : v_bcast(0.0f);
+      hr[i].WFY[c] = v_sel(hr[i].V[c] >= 0.0f, a, b);
     }
+    hr[i].WX[0] = v_ldg(wz, k * GX + cm2);
+    hr[i].WX[1] = v_ldg(wz, k * GX + cm1);
+    hr[i].WX[2] = v_ldg(wz, k * GX + cp1);
+    hr[i].WX[3] = v_ldg(wz, k * GX + cp2);
   }
 }
 
-// own rows + both halos of the field from any [GNC] buffer (global at the start of a circulation)
-GDEV void circ_load_field(CircTile& t, const WarpGeom& g, const float* X) {
+// x-direction part for one helper-owned (polar) row: all time2 diffusion sub-sub-steps (f:655-718)
+// and the polar advection (f:838-910)
+GDEV void helper_x(HelperRow& r, const HelperGeom& g, const GrebMemberConst& mc, int k) {
+  const float cc2 = mc.ccx2_diff[k], cca2 = mc.ccx2_adv[k];
+  const int time2 = mc.time2_diff[k];
+  XRow x;
+  xrow_products(x, r.T, r.W, r.WX, g.lane_l, g.lane_r);
+  vf S[3], h[3];
+  xdiff_bracket3(S, x);
   GUNROLL
-  for (int s = 0; s < GREB_MAXR + 4; ++s) {
-    const int k = g.k0 - 2 + s;
-    const bool ok = (k >= 0) && (k < GY) && (s < g.nr + 4);
+  for (int c = 0; c < 3; ++c) {
+    vf dd = div20(cc2 * S[c]);
+    dd = polar_clamp(dd, r.T[c]);  // f:715
+    h[c] = r.T[c] + dd;            // f:716
+  }
+  // polar advection bracket from the same products (f:872-878 + the f:881 index bug)
+  {
+    const vf dlo[3] = {x.dm1, x.d0, x.d1}, dhi[3] = {x.d0, x.d1, x.d2};
+    const vf wlo[3] = {r.WX[1], r.W[0], r.W[1]}, whi[3] = {r.W[1], r.W[2], r.WX[2]};
+    const vf P2[3] = {x.Pm2, x.Pm1, x.P0}, P3[3] = {x.Pm3, x.Pm2, x.Pm1};
+    const vf Qn1[3] = {x.Q1, x.Q2, x.Qp1}, Qn2[3] = {x.Q2, x.Qp1, x.Qp2};
     GUNROLL
-    for (int c = 0; c < 3; ++c) t.Y[s][c] = ok ? v_ld(X, k * GX + g.col + c) : v_bcast(0.0f);
-  }
-}
-
-// halo rows only, from the shared-memory copy written by the neighbouring warps
-GDEV void circ_load_halo(CircTile& t, const WarpGeom& g, const float* X) {
-  GUNROLL
-  for (int s = 0; s < GREB_MAXR + 4; ++s) {
-    const int k = g.k0 - 2 + s;
-    const bool halo = (s < 2) || (s >= g.nr + 2 && s < g.nr + 4);
-    if (halo && k >= 0 && k < GY) {
-      GUNROLL
-      for (int c = 0; c < 3; ++c) t.Y[s][c] = v_ld(X, k * GX + g.col + c);
+    for (int c = 0; c < 3; ++c) {
+      const vb pu = r.U[c] >= 0.0f;
+      const vf near10 = (10.0f * v_sel(pu, wlo[c], whi[c])) * v_sel(pu, dlo[c], dhi[c]);
+      vf mid = v_sel(pu, P2[c], Qn1[c]);
+      vf far = v_sel(pu, P3[c], Qn2[c]);
+      if (c == 0) {  // longitude 93 is cell 0 of lane 31: jp1 = jp2 = 94, jp3 = 0
+        const vb bug = g.is_bug && !pu;
+        mid = v_sel(bug, v_bcast(0.0f), mid);
+        far = v_sel(bug, r.WX[2] * (x.xp1 - r.T[1]), far);
+      }
+      const vf Sa = v_fma(4.0f, mid, near10) + far;
+      const vf Xu = (-r.U[c]) * Sa;
+      vf dd = div20(cca2 * Xu);
+      dd = polar_clamp(dd, r.T[c]);     // f:907
+      const vf ha = r.T[c] + dd;        // f:908
+      r.aTx[c] = ha - r.T[c];           // f:910
     }
   }
-}
-
-GDEV void circ_store_own(const CircTile& t, const WarpGeom& g, float* X) {
-  GUNROLL
-  for (int r = 0; r < GREB_MAXR; ++r) {
-    if (r < g.nr) {
-      GUNROLL
-      for (int c = 0; c < 3; ++c) v_st(X, (g.k0 + r) * GX + g.col + c, t.Y[r + 2][c]);
-    }
-  }
-}
-
-GDEV void circ_substep(CircTile& t, const WarpGeom& g, const GrebMemberConst& mc) {
-  vf Tn[GREB_MAXR][3];
-  GUNROLL
-  for (int r = 0; r < GREB_MAXR; ++r) {
-    if (r < g.nr) {
-      row_update(Tn[r], mc, g.k0 + r, t.Y[r], t.Y[r + 1], t.Y[r + 2], t.Y[r + 3], t.Y[r + 4], t.WY[r], t.WY[r + 1],
-                 t.WY[r + 2], t.WY[r + 3], t.WY[r + 4], t.WX[r], t.U[r], t.V[r], g.lane_l, g.lane_r, g.is_bug_lane);
+  GNOUNROLL
+  for (int tt2 = 1; tt2 < time2; ++tt2) {
+    XRow y;
+    xrow_products(y, h, r.W, r.WX, g.lane_l, g.lane_r);
+    xdiff_bracket3(S, y);
+    GUNROLL
+    for (int c = 0; c < 3; ++c) {
+      vf dd = div20(cc2 * S[c]);
+      dd = polar_clamp(dd, h[c]);
+      h[c] = h[c] + dd;
     }
   }
   GUNROLL
-  for (int r = 0; r < GREB_MAXR; ++r) {
-    if (r < g.nr) {
-      GUNROLL
-      for (int c = 0; c < 3; ++c) t.Y[r + 2][c] = Tn[r][c];
-    }
+  for (int c = 0; c < 3; ++c) r.dTx[c] = h[c] - r.T[c];  // f:718
+}
+
+// y-direction part + update of one helper-owned row (all five row cases of f:756-795, f:587-590)
+GDEV void helper_y(HelperRow& r, const HelperGeom& g, const GrebMemberConst& mc, int k, const float* buf) {
+  const float ccyd = mc.ccy_diff, ccya = mc.ccy_adv;
+  const int km1 = k >= 1 ? k - 1 : 0, km2 = k >= 2 ? k - 2 : 0;
+  const int kp1 = k <= GY - 2 ? k + 1 : GY - 1, kp2 = k <= GY - 3 ? k + 2 : GY - 1;
+  GUNROLL
+  for (int c = 0; c < 3; ++c) {
+    const vf T = r.T[c];
+    const vf tm1 = v_ld(buf, km1 * GX + g.col + c), tp1 = v_ld(buf, kp1 * GX + g.col + c);
+    const vf tm2 = v_ld(buf, km2 * GX + g.col + c), tp2 = v_ld(buf, kp2 * GX + g.col + c);
+    const vf Pym1 = r.Wm1[c] * (T - tm1);
+    const vf Qy0 = r.Wp1[c] * (tp1 - T);
+    vf dTy = ccyd * (Qy0 - Pym1);
+    if (k == 0) dTy = (ccyd * r.Wp1[c]) * (tp1 - T);       // f:589
+    if (k == GY - 1) dTy = (ccyd * r.Wm1[c]) * (tm1 - T);  // f:590
+    const vb pv = r.V[c] >= 0.0f;
+    const vf near = v_sel(pv, Pym1, -Qy0);
+    const vf far = r.WFY[c] * (T - v_sel(pv, tm2, tp2));
+    const vf Xv = (-v_abs(r.V[c])) * (near + far);
+    vf aTy = div3(ccya * Xv);                                              // rows 1, 3..ydim-2, ydim
+    if (k == 1) aTy = v_sel(pv, ccya * Xv, ccya * div3(Xv));               // f:766-769
+    if (k == GY - 2) aTy = v_sel(pv, ccya * div3(Xv), ccya * Xv);          // f:784-787
+    const vf dXd = r.W[c] * (r.dTx[c] + dTy);
+    const vf dXa = r.aTx[c] + aTy;
+    r.T[c] = (T + dXd) + dXa;
   }
 }
 
-// circulation (f:528-553): 24 sub-steps on the tile; `hb` = two [GNC] shared-memory buffers.
-// On entry the tile holds the field (own rows + halos); on exit the own rows hold X after 24
-// sub-steps.  All warps of the CTA must call it together (CTA barriers inside).
-GDEV void circulation_run(const SimtCtx& ctx, CircTile& t, const WarpGeom& g, const GrebMemberConst& mc, float* hb) {
+// =============================================================================================
+//                                     circulation drivers
+// =============================================================================================
+struct SyncState {
+  SplitBar* bar;
+  float* hb;    // [2][GNC]
+  float* smem;  // CTA shared memory base (private slots)
+  int phase;    // number of completed waits (runs on across circulations and steps)
+};
+
+// circulation (f:528-553) for a main-warp thread: on entry t.T holds X_in of the own cells, on exit
+// X after the 24 sub-steps (for rows whose circulation runs on a helper warp: read back from the
+// published field).  Every warp of the CTA (helpers via circulation_helper) must take part.
+GDEV void circulation_main(const SimtCtx& ctx, Tile& t, const RowGeom& g, const GrebMemberConst& mc, SyncState& ss) {
+  if (g.owned) tile_publish(t, g, ss.hb + (ss.phase & 1) * GNC);
+  sb_arrive(ctx, ss.bar);
   GNOUNROLL
   for (int tt = 0; tt < GSUB; ++tt) {
-    circ_substep(t, g, mc);
-    if (tt + 1 < GSUB) {
-      float* buf = hb + (tt & 1) * GNC;
-      circ_store_own(t, g, buf);
-      cta_sync(ctx);
-      circ_load_halo(t, g, buf);
-    }
+    vf dTx[GREB_CPT], aTx[GREB_CPT];
+    substep_x(dTx, aTx, t, g, mc);                    // own row only: overlaps the barrier latency
+    sb_wait(ctx, ss.bar, ss.phase);
+    const float* buf = ss.hb + (ss.phase & 1) * GNC;
+    if (g.ykind == 0) substep_y<false>(t, dTx, aTx, g, mc, buf, ss.smem);
+    else substep_y<true>(t, dTx, aTx, g, mc, buf, ss.smem);
+    ss.phase++;
+    if (g.owned) tile_publish(t, g, ss.hb + (ss.phase & 1) * GNC);   // also after the last sub-step
+    sb_arrive(ctx, ss.bar);
   }
+  sb_wait(ctx, ss.bar, ss.phase);   // everybody's final rows are published
+  if (!g.owned) tile_load_field(t, g, ss.hb + (ss.phase & 1) * GNC);
+  ss.phase++;
 }
 
-// ---------------------------------------------------------------------------------------------
-// Column physics + state update of one cell column (everything of time_loop / qflux_correction
-// that is not the circulation).  Phase A runs before the circulations, B after circulation(Ta),
-// C after circulation(q).
-// ---------------------------------------------------------------------------------------------
+GDEV void circulation_helper(const SimtCtx& ctx, HelperRow (&hr)[GREB_HROWS], const HelperGeom& g,
+                             const GrebMemberConst& mc, const float* X, SyncState& ss) {
+  GUNROLL
+  for (int i = 0; i < GREB_HROWS; ++i)
+    if (i < g.n) {
+      GUNROLL
+      for (int c = 0; c < 3; ++c) {
+        hr[i].T[c] = v_ld(X, g.k[i] * GX + g.col + c);
+        v_st(ss.hb + (ss.phase & 1) * GNC, g.k[i] * GX + g.col + c, hr[i].T[c]);
+      }
+    }
+  sb_arrive(ctx, ss.bar);
+  GNOUNROLL
+  for (int tt = 0; tt < GSUB; ++tt) {
+    GUNROLL
+    for (int i = 0; i < GREB_HROWS; ++i)
+      if (i < g.n) helper_x(hr[i], g, mc, g.k[i]);
+    sb_wait(ctx, ss.bar, ss.phase);
+    const float* buf = ss.hb + (ss.phase & 1) * GNC;
+    ss.phase++;
+    float* nxt = ss.hb + (ss.phase & 1) * GNC;
+    GUNROLL
+    for (int i = 0; i < GREB_HROWS; ++i)
+      if (i < g.n) {
+        helper_y(hr[i], g, mc, g.k[i], buf);
+        GUNROLL
+        for (int c = 0; c < 3; ++c) v_st(nxt, g.k[i] * GX + g.col + c, hr[i].T[c]);
+      }
+    sb_arrive(ctx, ss.bar);
+  }
+  sb_wait(ctx, ss.bar, ss.phase);
+  ss.phase++;
+}
+
+// =============================================================================================
+//        column physics + state update (everything of time_loop / qflux_correction that is not
+//        the circulation), 4 consecutive cells at a time
+// =============================================================================================
 GDEV vf pow4(vf x) {
   const vf x2 = x * x;
   return x2 * x2;  // gfortran expands x**4 as (x*x)*(x*x)
 }
 
 struct StepInfo {
-  int ityr;     // 0-based step of year
+  int ityr;       // 0-based step of year
   int month_end;  // 1 if a month ends at this step (f:975-976)
-  float ndm;    // days of that month * 2
-  int out_rec;  // month slot of this launch to write
+  float ndm;      // days of that month * 2
+  int out_rec;    // month slot of this launch to write
   float co2;
   int spinup;
 };
 
-GDEV void column_phase_a(const SimtCtx& ctx, const GrebKernelArgs& a, const GrebMemberConst& mc, int member,
-                         const StepInfo& si, int k, vi col, float* stash) {
+// Phase A (before the circulations): SW, LW, sensible, hydro, deep ocean; Ts/To/cap_surf update,
+// flux corrections in spin-up mode; stashes the air-temperature and humidity tendencies.
+GDEV void column_phase_a(const GrebKernelArgs& a, const GrebMemberConst& mc, int member, const StepInfo& si, int k,
+                         vi idx0, float* stash) {
   const float* forc = a.forc + (size_t)si.ityr * GF_COUNT * GNC;
   float* st = a.state + (size_t)member * GS_COUNT * GNC;
   float* acc = a.acc + (size_t)member * GA_COUNT * GNC;
@@ -453,18 +614,43 @@ GDEV void column_phase_a(const SimtCtx& ctx, const GrebKernelArgs& a, const Greb
   float* corr = a.corr + ((size_t)mc.group * GNT + si.ityr) * GC_COUNT * GNC;
   const float solar = a.sw_solar[si.ityr * GY + k];
   const float* pe = mc.p_emi;
+
+  vf Ts4[4], Ta4[4], To4[4], q4[4], cap4[4], cld4[4], dTrad4[4], swet4[4], absw4[4], mld4[4], dmld4[4], zoc4[4], ez4[4];
+  vf c1[4], c2[4], tsmn4[4], tmm4[4], tomm4[4], apmm4[4];
+  vi mask4[4];
+  v_ld4(Ts4, st + GS_TS * GNC, idx0);
+  v_ld4(Ta4, st + GS_TA * GNC, idx0);
+  v_ld4(To4, st + GS_TO * GNC, idx0);
+  v_ld4(q4, st + GS_Q * GNC, idx0);
+  v_ld4(cap4, st + GS_CAP * GNC, idx0);
+  v_ldg4(cld4, forc + GF_CLD * GNC, idx0);
+  v_ldg4(dTrad4, forc + GF_DTRAD * GNC, idx0);
+  v_ldg4(swet4, forc + GF_SWET * GNC, idx0);
+  v_ldg4(absw4, forc + GF_ABSWIND * GNC, idx0);
+  v_ldg4(mld4, forc + GF_MLD * GNC, idx0);
+  v_ldg4(dmld4, forc + GF_DMLD * GNC, idx0);
+  v_ldgi4(mask4, a.mask, idx0);
+  v_ldg4(zoc4, a.z_ocean, idx0);
+  v_ldg4(ez4, wz_air, idx0);
+  if (!si.spinup) {
+    v_ld4(c1, corr + GC_TF * GNC, idx0);
+    v_ld4(c2, corr + GC_TOF * GNC, idx0);
+    v_ld4(tmm4, acc + GA_TMM * GNC, idx0);
+    v_ld4(tomm4, acc + GA_TOMM * GNC, idx0);
+    v_ld4(apmm4, acc + GA_APMM * GNC, idx0);
+  } else {
+    v_ldg4(c1, a.tclim + (size_t)si.ityr * GNC, idx0);
+    v_ldg4(c2, a.toclim, idx0);
+  }
+  v_ld4(tsmn4, acc + GA_TSMN * GNC, idx0);
+
+  vf Ts0o[4], To0o[4], capo4[4], tendA4[4], tq4[4], tfo[4], tofo[4], albo[4];
   GUNROLL
-  for (int c = 0; c < 3; ++c) {
-    const vi idx = k * GX + col + c;
-    const vf Ts = v_ld(st + GS_TS * GNC, idx), Ta = v_ld(st + GS_TA * GNC, idx);
-    const vf To = v_ld(st + GS_TO * GNC, idx), q = v_ld(st + GS_Q * GNC, idx);
-    const vf cap = v_ld(st + GS_CAP * GNC, idx);
-    const vf cld = v_ldg(forc + GF_CLD * GNC, idx), dTrad = v_ldg(forc + GF_DTRAD * GNC, idx);
-    const vf swet = v_ldg(forc + GF_SWET * GNC, idx), absw = v_ldg(forc + GF_ABSWIND * GNC, idx);
-    const vf mld = v_ldg(forc + GF_MLD * GNC, idx), dmld = v_ldg(forc + GF_DMLD * GNC, idx);
-    const vi mask = v_ldgi(a.mask, idx);
-    const vf zoc = v_ldg(a.z_ocean, idx), ez = v_ldg(wz_air, idx);
-    const vb land_ge0 = v_bit(mask, 0), ocean = v_bit(mask, 1), glac = v_bit(mask, 2);
+  for (int i = 0; i < 4; ++i) {
+    const vf Ts = Ts4[i], Ta = Ta4[i], To = To4[i], q = q4[i], cap = cap4[i];
+    const vf cld = cld4[i], dTrad = dTrad4[i], swet = swet4[i], absw = absw4[i], mld = mld4[i], dmld = dmld4[i];
+    const vf zoc = zoc4[i], ez = ez4[i];
+    const vb land_ge0 = v_bit(mask4[i], 0), ocean = v_bit(mask4[i], 1), glac = v_bit(mask4[i], 2);
 
     // ---- SWradiation, f:380-401
     const vf a_atmos = cld * mc.a_cloud;
@@ -509,26 +695,24 @@ GDEV void column_phase_a(const SimtCtx& ctx, const GrebKernelArgs& a, const Greb
     dTo = dTo + GREB_DT * mc.co_turb * (Tx - To) / (mc.cap_ocean * (zoc - mld));
     dToc = dToc + GREB_DT * mc.co_turb * (To - Tx) / (mc.cap_ocean * mld);
 
-    vf Ts0, To0, tendA, tq;
-    if (!si.spinup) {  // time_loop, f:258-264
-      const vf TF = v_ld(corr + GC_TF * GNC, idx), ToF = v_ld(corr + GC_TOF * GNC, idx);
-      Ts0 = Ts + dToc + GREB_DT * (sw + LWsurf - LWdown + Qlat + Qsens + TF) / cap;
-      tendA = GREB_DT * (LWup + LWdown - em * LWsurf + Qlat_air - Qsens) / mc.cap_air;
-      To0 = To + dTo + ToF;
-      tq = GREB_DT * (dq_eva + dq_rain);
+    vf Ts0, To0;
+    tendA4[i] = GREB_DT * (LWup + LWdown - em * LWsurf + Qlat_air - Qsens) / mc.cap_air;  // f:260 / f:336
+    tq4[i] = GREB_DT * (dq_eva + dq_rain);                                                // f:264 / f:341
+    if (!si.spinup) {  // time_loop, f:258-262
+      Ts0 = Ts + dToc + GREB_DT * (sw + LWsurf - LWdown + Qlat + Qsens + c1[i]) / cap;
+      To0 = To + dTo + c2[i];
+      tfo[i] = c1[i];
+      tofo[i] = c2[i];
     } else {  // qflux_correction, f:333-351
-      const vf Tclim = v_ldg(a.tclim + (size_t)si.ityr * GNC, idx), Toclim = v_ldg(a.toclim, idx);
       const vf dTs = GREB_DT * (sw + LWsurf - LWdown + Qlat + Qsens) / cap;
       const vf ts0 = Ts + dTs + dToc;
-      tendA = GREB_DT * (LWup + LWdown - em * LWsurf + Qlat_air - Qsens) / mc.cap_air;
       const vf to0 = To + dTo;
-      tq = GREB_DT * (dq_eva + dq_rain);
-      const vf T_error = Tclim - ts0;
+      const vf T_error = c1[i] - ts0;
       const vf tf = T_error * cap / GREB_DT;
-      v_st(corr + GC_TF * GNC, idx, tf);
+      tfo[i] = tf;
       Ts0 = Ts + dTs + dToc + tf * GREB_DT / cap;
-      const vf tof = Toclim - to0;
-      v_st(corr + GC_TOF * GNC, idx, tof);
+      const vf tof = c2[i] - to0;
+      tofo[i] = tof;
       To0 = To + dTo + tof;
     }
 
@@ -542,80 +726,92 @@ GDEV void column_phase_a(const SimtCtx& ctx, const GrebKernelArgs& a, const Greb
       capn = v_sel(ocean, ramp, capn);
       capn = v_sel(glac, v_bcast(mc.cap_land), capn);
     }
-
-    v_st(st + GS_TS * GNC, idx, Ts0);
-    v_st(st + GS_TO * GNC, idx, To0);
-    v_st(st + GS_CAP * GNC, idx, capn);
-    v_st(stash, idx, tendA);
-    v_st(stash + GNC, idx, tq);
-    // diagnostics (f:945) runs in both loops; output (f:974) only in time_loop
-    v_st(acc + GA_TSMN * GNC, idx, v_ld(acc + GA_TSMN * GNC, idx) + Ts0);
-    if (!si.spinup) {
-      v_st(acc + GA_TMM * GNC, idx, v_ld(acc + GA_TMM * GNC, idx) + Ts0);
-      v_st(acc + GA_TOMM * GNC, idx, v_ld(acc + GA_TOMM * GNC, idx) + To0);
-      v_st(acc + GA_APMM * GNC, idx, v_ld(acc + GA_APMM * GNC, idx) + albedo);
-    }
+    Ts0o[i] = Ts0;
+    To0o[i] = To0;
+    capo4[i] = capn;
+    albo[i] = albedo;
+  }
+  v_st4(st + GS_TS * GNC, idx0, Ts0o[0], Ts0o[1], Ts0o[2], Ts0o[3]);
+  v_st4(st + GS_TO * GNC, idx0, To0o[0], To0o[1], To0o[2], To0o[3]);
+  v_st4(st + GS_CAP * GNC, idx0, capo4[0], capo4[1], capo4[2], capo4[3]);
+  v_st4(stash, idx0, tendA4[0], tendA4[1], tendA4[2], tendA4[3]);
+  v_st4(stash + GNC, idx0, tq4[0], tq4[1], tq4[2], tq4[3]);
+  // diagnostics (f:945) runs in both loops; output (f:974) only in time_loop
+  v_st4(acc + GA_TSMN * GNC, idx0, tsmn4[0] + Ts0o[0], tsmn4[1] + Ts0o[1], tsmn4[2] + Ts0o[2], tsmn4[3] + Ts0o[3]);
+  if (!si.spinup) {
+    v_st4(acc + GA_TMM * GNC, idx0, tmm4[0] + Ts0o[0], tmm4[1] + Ts0o[1], tmm4[2] + Ts0o[2], tmm4[3] + Ts0o[3]);
+    v_st4(acc + GA_TOMM * GNC, idx0, tomm4[0] + To0o[0], tomm4[1] + To0o[1], tomm4[2] + To0o[2], tomm4[3] + To0o[3]);
+    v_st4(acc + GA_APMM * GNC, idx0, apmm4[0] + albo[0], apmm4[1] + albo[1], apmm4[2] + albo[2], apmm4[3] + albo[3]);
+  } else {
+    v_st4(corr + GC_TF * GNC, idx0, tfo[0], tfo[1], tfo[2], tfo[3]);
+    v_st4(corr + GC_TOF * GNC, idx0, tofo[0], tofo[1], tofo[2], tofo[3]);
   }
 }
 
-// after circulation(Ta): X holds the circulated air temperature of the 3 cells of row k
-GDEV void column_phase_b(const GrebKernelArgs& a, int member, const StepInfo& si, int k, vi col, const vf (&X)[3],
+// Phase B: after circulation(Ta).  X = circulated air temperature of 4 cells.
+GDEV void column_phase_b(const GrebKernelArgs& a, int member, const StepInfo& si, vi idx0, const vf* X,
                          const float* stash) {
   float* st = a.state + (size_t)member * GS_COUNT * GNC;
   float* acc = a.acc + (size_t)member * GA_COUNT * GNC;
+  vf Ta1[4], tendA[4], tamm[4], o[4];
+  v_ld4(Ta1, st + GS_TA * GNC, idx0);
+  v_ld4(tendA, stash, idx0);
+  if (!si.spinup) v_ld4(tamm, acc + GA_TAMM * GNC, idx0);
   GUNROLL
-  for (int c = 0; c < 3; ++c) {
-    const vi idx = k * GX + col + c;
-    const vf Ta1 = v_ld(st + GS_TA * GNC, idx);
-    const vf dTa_crcl = X[c] - Ta1;  // f:551
-    const vf tendA = v_ld(stash, idx);
-    const vf Ta0 = si.spinup ? (Ta1 + tendA + dTa_crcl)    // f:337
-                             : (Ta1 + dTa_crcl + tendA);   // f:260
-    v_st(st + GS_TA * GNC, idx, Ta0);
-    if (!si.spinup) v_st(acc + GA_TAMM * GNC, idx, v_ld(acc + GA_TAMM * GNC, idx) + Ta0);
+  for (int i = 0; i < 4; ++i) {
+    const vf dTa_crcl = X[i] - Ta1[i];                       // f:551
+    o[i] = si.spinup ? (Ta1[i] + tendA[i] + dTa_crcl)        // f:337
+                     : (Ta1[i] + dTa_crcl + tendA[i]);       // f:260
   }
+  v_st4(st + GS_TA * GNC, idx0, o[0], o[1], o[2], o[3]);
+  if (!si.spinup) v_st4(acc + GA_TAMM * GNC, idx0, tamm[0] + o[0], tamm[1] + o[1], tamm[2] + o[2], tamm[3] + o[3]);
 }
 
-// after circulation(q)
-GDEV void column_phase_c(const GrebKernelArgs& a, const GrebMemberConst& mc, int member, const StepInfo& si, int k,
-                         vi col, const vf (&X)[3], const float* stash) {
+// Phase C: after circulation(q)
+GDEV void column_phase_c(const GrebKernelArgs& a, const GrebMemberConst& mc, int member, const StepInfo& si, vi idx0,
+                         const vf* X, const float* stash) {
   float* st = a.state + (size_t)member * GS_COUNT * GNC;
   float* acc = a.acc + (size_t)member * GA_COUNT * GNC;
   float* corr = a.corr + ((size_t)mc.group * GNT + si.ityr) * GC_COUNT * GNC;
-  GUNROLL
-  for (int c = 0; c < 3; ++c) {
-    const vi idx = k * GX + col + c;
-    const vf q1 = v_ld(st + GS_Q * GNC, idx);
-    const vf dq_crcl = X[c] - q1;  // f:551
-    const vf tq = v_ld(stash + GNC, idx);
-    vf q0;
-    if (!si.spinup) {  // f:264-266
-      vf dq = tq + dq_crcl + v_ld(corr + GC_QF * GNC, idx);
-      dq = v_sel(dq <= -q1, -0.9f * q1, dq);
-      q0 = q1 + dq;
-      v_st(acc + GA_QMM * GNC, idx, v_ld(acc + GA_QMM * GNC, idx) + q0);
-    } else {  // f:342, 353-355
-      const vf qq0 = q1 + tq + dq_crcl;
-      const vf qf = v_ldg(a.qclim + (size_t)si.ityr * GNC, idx) - qq0;
-      v_st(corr + GC_QF * GNC, idx, qf);
-      q0 = q1 + tq + dq_crcl + qf;
-    }
-    v_st(st + GS_Q * GNC, idx, q0);
+  vf q1[4], tq[4], cq[4], qmm[4], o[4], qfo[4];
+  v_ld4(q1, st + GS_Q * GNC, idx0);
+  v_ld4(tq, stash + GNC, idx0);
+  if (!si.spinup) {
+    v_ld4(cq, corr + GC_QF * GNC, idx0);
+    v_ld4(qmm, acc + GA_QMM * GNC, idx0);
+  } else {
+    v_ldg4(cq, a.qclim + (size_t)si.ityr * GNC, idx0);
   }
+  GUNROLL
+  for (int i = 0; i < 4; ++i) {
+    const vf dq_crcl = X[i] - q1[i];  // f:551
+    if (!si.spinup) {                 // f:264-266
+      vf dq = tq[i] + dq_crcl + cq[i];
+      dq = v_sel(dq <= -q1[i], -0.9f * q1[i], dq);
+      o[i] = q1[i] + dq;
+      qfo[i] = cq[i];
+    } else {  // f:342, 353-355
+      const vf qq0 = q1[i] + tq[i] + dq_crcl;
+      const vf qf = cq[i] - qq0;
+      qfo[i] = qf;
+      o[i] = q1[i] + tq[i] + dq_crcl + qf;
+    }
+  }
+  v_st4(st + GS_Q * GNC, idx0, o[0], o[1], o[2], o[3]);
+  if (!si.spinup) v_st4(acc + GA_QMM * GNC, idx0, qmm[0] + o[0], qmm[1] + o[1], qmm[2] + o[2], qmm[3] + o[3]);
+  else v_st4(corr + GC_QF * GNC, idx0, qfo[0], qfo[1], qfo[2], qfo[3]);
 }
 
-// month end (f:977-983): write the five means, zero the accumulators
-GDEV void column_month_end(const GrebKernelArgs& a, int member, const StepInfo& si, int k, vi col) {
+// month end (f:977-983): write the five means (16-byte coalesced stores), zero the accumulators
+GDEV void column_month_end(const GrebKernelArgs& a, int member, const StepInfo& si, vi idx0) {
   float* acc = a.acc + (size_t)member * GA_COUNT * GNC;
   float* out = a.out ? a.out + ((size_t)member * a.out_months + si.out_rec) * 5 * GNC : nullptr;
   GUNROLL
-  for (int c = 0; c < 3; ++c) {
-    const vi idx = k * GX + col + c;
-    GUNROLL
-    for (int f = 0; f < 5; ++f) {
-      if (out) v_st(out + f * GNC, idx, v_ld(acc + f * GNC, idx) / si.ndm);
-      v_st(acc + f * GNC, idx, v_bcast(0.0f));
-    }
+  for (int f = 0; f < 5; ++f) {
+    vf x[4];
+    v_ld4(x, acc + f * GNC, idx0);
+    if (out) v_st4(out + f * GNC, idx0, x[0] / si.ndm, x[1] / si.ndm, x[2] / si.ndm, x[3] / si.ndm);
+    v_st4(acc + f * GNC, idx0, v_bcast(0.0f), v_bcast(0.0f), v_bcast(0.0f), v_bcast(0.0f));
   }
 }
 
@@ -636,12 +832,10 @@ GDEV StepInfo step_info(const GrebKernelArgs& a, const GrebMemberConst& mc, int 
         si.ndm = (float)(dim[m] * 2);
       }
   }
-  // months completed before this step since the launch began (launches start on a year boundary
-  // or anywhere: count month ends in (it0-1, it-1])
+  // month ends in [it0, it): the slot of this launch's output buffer to write
   int rec = 0;
   {
     const int first = a.it0;
-    // month ends occur at it = 730*y + 2*cum[m]
     const int y0 = (first - 1) / GNT, y1 = (it - 1) / GNT;
     for (int y = y0; y <= y1; ++y)
       for (int m = 0; m < 12; ++m) {
@@ -654,17 +848,19 @@ GDEV StepInfo step_info(const GrebKernelArgs& a, const GrebMemberConst& mc, int 
   return si;
 }
 
-// ---------------------------------------------------------------------------------------------
+// =============================================================================================
 // The whole member integration: `nsteps` steps starting at step counter it0.
-// smem layout: [0, 2*GNC) halo double buffer, [2*GNC, 4*GNC) stash (tendA, tq).
-// ---------------------------------------------------------------------------------------------
-GDEV void member_run(const SimtCtx& ctx, const GrebKernelArgs& a, const GrebMemberConst& mc, int member) {
-  float* hb = ctx.smem;
-  float* stash = ctx.smem + 2 * GNC;
-  const WarpGeom g = warp_geom(ctx, mc);
+// `smem` layout: greb_types.h GSM_*.  The SplitBar and the flags must have been initialised
+// (sb_init with the number of arriving units, flags = 0) before the first call.
+// =============================================================================================
+GDEV void member_run_main(const SimtCtx& ctx, const GrebKernelArgs& a, const GrebMemberConst& mc, int member,
+                          SyncState& ss) {
+  float* smem = ctx.smem;
+  float* stash = smem + GSM_STASH;
   float* st = a.state + (size_t)member * GS_COUNT * GNC;
   const float* wzg = a.wz + (size_t)mc.group * 2 * GNC;
-  CircTile t;
+  const RowGeom g = row_geom(ctx, mc);
+  Tile t;
 
   GNOUNROLL
   for (int it = a.it0; it < a.it0 + a.nsteps; ++it) {
@@ -673,45 +869,42 @@ GDEV void member_run(const SimtCtx& ctx, const GrebKernelArgs& a, const GrebMemb
 
     // ---- phase A: column physics, Ts/To/cap update
     GNOUNROLL
-    for (int r = 0; r < g.nr; ++r) column_phase_a(ctx, a, mc, member, si, g.k0 + r, g.col, stash);
+    for (int q = 0; q < 3; ++q) column_phase_a(a, mc, member, si, g.k, g.k * GX + g.col + 4 * q, stash);
+    tile_load_uv(t, g, forc + GF_U * GNC, forc + GF_V * GNC, smem);
+    // the helper warps read the rows they circulate from global state written by the main warps
+    cta_sync(ctx);
 
     // ---- circulation of air temperature (f:301), then of humidity (f:303): one code instance
-    circ_load_uv(t, g, forc + GF_U * GNC, forc + GF_V * GNC);
     GNOUNROLL
     for (int fld = 0; fld < 2; ++fld) {
-      circ_load_wz(t, g, wzg + fld * GNC);
-      circ_load_field(t, g, st + (fld == 0 ? GS_TA : GS_Q) * GNC);
-      circulation_run(ctx, t, g, mc, hb);
-      if (fld == 0) {
-        GUNROLL
-        for (int r = 0; r < GREB_MAXR; ++r)
-          if (r < g.nr) column_phase_b(a, member, si, g.k0 + r, g.col, t.Y[r + 2], stash);
-        cta_sync(ctx);  // halo buffers are reused by the next circulation
-      } else {
-        GUNROLL
-        for (int r = 0; r < GREB_MAXR; ++r)
-          if (r < g.nr) column_phase_c(a, mc, member, si, g.k0 + r, g.col, t.Y[r + 2], stash);
+      tile_load_wz(t, g, wzg + fld * GNC, smem);
+      tile_load_field(t, g, st + (fld == 0 ? GS_TA : GS_Q) * GNC);
+      circulation_main(ctx, t, g, mc, ss);
+      GUNROLL
+      for (int q = 0; q < 3; ++q) {
+        if (fld == 0) column_phase_b(a, member, si, g.k * GX + g.col + 4 * q, &t.T[4 * q], stash);
+        else column_phase_c(a, mc, member, si, g.k * GX + g.col + 4 * q, &t.T[4 * q], stash);
       }
     }
 
     // ---- output (f:975-985)
     if (!si.spinup && si.month_end) {
       GNOUNROLL
-      for (int r = 0; r < g.nr; ++r) column_month_end(a, member, si, g.k0 + r, g.col);
+      for (int q = 0; q < 3; ++q) column_month_end(a, member, si, g.k * GX + g.col + 4 * q);
     }
 
     // ---- annual mean diagnostics (f:948-956)
     if (si.ityr == GNT - 1) {
       float* acc = a.acc + (size_t)member * GA_COUNT * GNC;
-      cta_sync(ctx);
-      GNOUNROLL
-      for (int r = 0; r < g.nr; ++r) {
-        GUNROLL
-        for (int c = 0; c < 3; ++c) {
-          const vi idx = (g.k0 + r) * GX + g.col + c;
-          v_st(hb, idx, v_ld(acc + GA_TSMN * GNC, idx) / (float)GNT);  // f:949
-          v_st(acc + GA_TSMN * GNC, idx, v_bcast(0.0f));               // f:955
-        }
+      float* scratch = ss.hb;
+      cta_sync(ctx);  // every thread is past its last read of the field buffers
+      GUNROLL
+      for (int q = 0; q < 3; ++q) {
+        vf x[4];
+        const vi idx0 = g.k * GX + g.col + 4 * q;
+        v_ld4(x, acc + GA_TSMN * GNC, idx0);
+        v_st4(scratch, idx0, x[0] / (float)GNT, x[1] / (float)GNT, x[2] / (float)GNT, x[3] / (float)GNT);  // f:949
+        v_st4(acc + GA_TSMN * GNC, idx0, v_bcast(0.0f), v_bcast(0.0f), v_bcast(0.0f), v_bcast(0.0f));     // f:955
       }
       cta_sync(ctx);
       if (ctx.warp == 0 && lane0(ctx)) {
@@ -719,8 +912,8 @@ GDEV void member_run(const SimtCtx& ctx, const GrebKernelArgs& a, const GrebMemb
         for (int k = 0; k < GY; ++k) {
           float rs = 0.0f;
           for (int i = 0; i < GX; ++i) {
-            s = s + hb[k * GX + i];  // f:954 sum() in array element order
-            rs = rs + hb[k * GX + i];
+            s = s + scratch[k * GX + i];  // f:954 sum() in array element order
+            rs = rs + scratch[k * GX + i];
           }
           sw = sw + a.coslat_w[k] * (rs / (float)GX);
         }
@@ -729,7 +922,43 @@ GDEV void member_run(const SimtCtx& ctx, const GrebKernelArgs& a, const GrebMemb
         a.diag[member * 2 + 1] = sw - 273.15f;
         if (!(g0 == g0) || g0 > 1e4f || g0 < -1e4f) a.flags[member] = 1;
       }
+      cta_sync(ctx);  // scratch (= field buffer) is free again
     }
-    cta_sync(ctx);  // next step's phase A may overwrite the stash / reuse hb
   }
+}
+
+// the helper warps' view of the same step sequence (identical barrier pattern)
+GDEV void member_run_helper(const SimtCtx& ctx, const GrebKernelArgs& a, const GrebMemberConst& mc, int member,
+                            SyncState& ss) {
+  const float* st = a.state + (size_t)member * GS_COUNT * GNC;
+  const float* wzg = a.wz + (size_t)mc.group * 2 * GNC;
+  const HelperGeom hg = helper_geom(ctx, mc);
+  HelperRow hr[GREB_HROWS];
+  GNOUNROLL
+  for (int it = a.it0; it < a.it0 + a.nsteps; ++it) {
+    const int ityr = (it - 1) % GNT;
+    const float* forc = a.forc + (size_t)ityr * GF_COUNT * GNC;
+    helper_load_uv(hr, hg, forc + GF_U * GNC, forc + GF_V * GNC);
+    cta_sync(ctx);
+    GNOUNROLL
+    for (int fld = 0; fld < 2; ++fld) {
+      helper_load_wz(hr, hg, wzg + fld * GNC);
+      circulation_helper(ctx, hr, hg, mc, st + (fld == 0 ? GS_TA : GS_Q) * GNC, ss);
+    }
+    if (ityr == GNT - 1) {
+      cta_sync(ctx);
+      cta_sync(ctx);
+      cta_sync(ctx);
+    }
+  }
+}
+
+GDEV void member_run(const SimtCtx& ctx, const GrebKernelArgs& a, const GrebMemberConst& mc, int member) {
+  SyncState ss;
+  ss.bar = reinterpret_cast<SplitBar*>(ctx.smem + GSM_SYNC);
+  ss.hb = ctx.smem + GSM_HB;
+  ss.smem = ctx.smem;
+  ss.phase = 0;
+  if (ctx_is_helper(ctx)) member_run_helper(ctx, a, mc, member, ss);
+  else member_run_main(ctx, a, mc, member, ss);
 }

@@ -122,61 +122,45 @@ void greb_build_forcing(GrebHostForcing& F, const float* z_topo, const float* gl
 
 static int f_nint(float x) { return (int)lroundf(x); }
 
-void greb_partition_rows(const int* polar, const int* time2_diff, const int* time2_adv, int* row0, int* nrow) {
-  // issue-slot model per cell and sub-step: main row 51, polar row 61, +25 per extra
-  // diffusion sub-sub-step, +22 per extra advection sub-sub-step
-  int cost[GY];
-  for (int k = 0; k < GY; ++k)
-    cost[k] = (polar[k] ? 61 : 51) + 25 * (time2_diff[k] - 1) + 22 * (time2_adv[k] - 1);
-  // DP: split rows 0..47 into GREB_NWARP contiguous bands of 1..GREB_MAXR rows minimising the
-  // sum of squared band costs
-  const double INF = 1e300;
-  static double best[GREB_NWARP + 1][GY + 1];
-  static int from[GREB_NWARP + 1][GY + 1];
-  for (int b = 0; b <= GREB_NWARP; ++b)
-    for (int k = 0; k <= GY; ++k) best[b][k] = INF;
-  best[0][0] = 0;
-  for (int b = 1; b <= GREB_NWARP; ++b)
-    for (int k = 1; k <= GY; ++k)
-      for (int n = 1; n <= GREB_MAXR && n <= k; ++n) {
-        if (best[b - 1][k - n] >= INF) continue;
-        double c = 0;
-        for (int j = k - n; j < k; ++j) c += cost[j];
-        const double v = best[b - 1][k - n] + c * c;
-        if (v < best[b][k]) {
-          best[b][k] = v;
-          from[b][k] = n;
-        }
-      }
-  int b0[GREB_NWARP], bn[GREB_NWARP], bc[GREB_NWARP];
-  for (int b = GREB_NWARP, k = GY; b >= 1; --b) {
-    const int n = from[b][k];
-    bn[b - 1] = n;
-    b0[b - 1] = k - n;
-    k -= n;
+int greb_assign_rows(const int* polar, const int* time2_diff, const int* time2_adv, int* row_of_group,
+                     int* hslot_of_row, int* helper_row, int* n_hslots) {
+  // Lane groups (4 per main warp) -> rows.  Warps are kept homogeneous (all polar-branch rows or all
+  // main-branch rows) so that the f:592/f:799 branch does not diverge inside a warp; the cheaper
+  // main-row warps go to the SM sub-partitions (warp % 4) that also host a helper warp (12, 13).
+  int pol[GY], mainr[GY], np = 0, nm = 0;
+  for (int k = 0; k < GY; ++k) (polar[k] ? pol[np++] : mainr[nm++]) = k;
+  int rows[GY], n = 0;  // rows in group order of a virtual warp list: polar warps first
+  for (int i = 0; i < np; ++i) rows[n++] = pol[i];
+  for (int i = 0; i < nm; ++i) rows[n++] = mainr[i];
+  const int n_polar_warps = (np + 3) / 4;
+  // physical warp order: polar warps take ids with (w % 4) in {2, 3} first
+  int order[GREB_NMAIN], no = 0;
+  for (int w = 0; w < GREB_NMAIN; ++w)
+    if ((w & 3) >= 2) order[no++] = w;
+  for (int w = 0; w < GREB_NMAIN; ++w)
+    if ((w & 3) < 2) order[no++] = w;
+  (void)n_polar_warps;
+  for (int v = 0; v < GREB_NMAIN; ++v)
+    for (int s = 0; s < 4; ++s) row_of_group[order[v] * 4 + s] = rows[v * 4 + s];
+  // helper-owned rows: the two pole rows (always) and every row whose polar diffusion needs more
+  // than one sub-sub-step; the helper code implements the polar branch only
+  int nh = 0;
+  for (int k = 0; k < GY; ++k) {
+    hslot_of_row[k] = -1;
+    if (time2_adv[k] > 1) return -2;  // cannot happen on the 96x48 grid (f:838: dd = 1 for every row)
+    if (k == 0 || k == GY - 1 || time2_diff[k] > 1) {
+      if (!polar[k]) return -3;
+      if (nh >= GREB_MAXH) return -1;
+      hslot_of_row[k] = nh;
+      helper_row[nh++] = k;
+    }
   }
-  for (int b = 0; b < GREB_NWARP; ++b) {
-    bc[b] = 0;
-    for (int j = b0[b]; j < b0[b] + bn[b]; ++j) bc[b] += cost[j];
-  }
-  // bands -> warps: longest-processing-time first into the 4 sub-partitions, 3 warps each
-  int order[GREB_NWARP];
-  for (int b = 0; b < GREB_NWARP; ++b) order[b] = b;
-  std::stable_sort(order, order + GREB_NWARP, [&](int x, int y) { return bc[x] > bc[y]; });
-  int load[4] = {0, 0, 0, 0}, cnt[4] = {0, 0, 0, 0};
-  for (int i = 0; i < GREB_NWARP; ++i) {
-    int bestq = -1;
-    for (int q = 0; q < 4; ++q)
-      if (cnt[q] < GREB_NWARP / 4 && (bestq < 0 || load[q] < load[bestq])) bestq = q;
-    const int w = bestq + 4 * cnt[bestq];
-    row0[w] = b0[order[i]];
-    nrow[w] = bn[order[i]];
-    load[bestq] += bc[order[i]];
-    cnt[bestq]++;
-  }
+  for (int s = nh; s < GREB_MAXH; ++s) helper_row[s] = 0;
+  *n_hslots = nh;
+  return 0;
 }
 
-void greb_build_member_const(GrebMemberConst& mc, const greb_physics_par& p, int group) {
+int greb_build_member_const(GrebMemberConst& mc, const greb_physics_par& p, int group) {
   memset(&mc, 0, sizeof mc);
   mc.sig = p.sig; mc.ct_sens = p.ct_sens; mc.da_ice = p.da_ice; mc.a_no_ice = p.a_no_ice; mc.a_cloud = p.a_cloud;
   mc.Tl_ice1 = p.Tl_ice1; mc.Tl_ice2 = p.Tl_ice2; mc.To_ice1 = p.To_ice1; mc.To_ice2 = p.To_ice2;
@@ -216,7 +200,8 @@ void greb_build_member_const(GrebMemberConst& mc, const greb_physics_par& p, int
       mc.ccx2_adv[k - 1] = (float)dtdff2 / dxlat / 2.f;
     }
   }
-  greb_partition_rows(mc.polar, mc.time2_diff, mc.time2_adv, mc.row0, mc.nrow);
+  return greb_assign_rows(mc.polar, mc.time2_diff, mc.time2_adv, mc.row_of_group, mc.hslot_of_row, mc.helper_row,
+                          &mc.n_hslots);
 }
 
 void greb_build_wz(float* out, const GrebHostForcing& F, const greb_physics_par& p) {

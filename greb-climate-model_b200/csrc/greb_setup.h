@@ -29,8 +29,10 @@ void greb_build_forcing(GrebHostForcing& F, const float* z_topo, const float* gl
                         const float* tclim, const float* qclim, const float* swetclim, const float* uclim,
                         const float* vclim, const float* mldclim, const float* cldclim);
 
-// physics scalars, heat capacities (f:186-188), circulation geometry and the row partition
-void greb_build_member_const(GrebMemberConst& mc, const greb_physics_par& p, int group);
+// physics scalars, heat capacities (f:186-188), circulation geometry and the row assignment.
+// Returns 0, or <0 if the geometry needs more helper rows than the kernel supports (kappa far
+// outside the reference's range) or sub-stepped polar advection (impossible at 96x48).
+int greb_build_member_const(GrebMemberConst& mc, const greb_physics_par& p, int group);
 
 // wz_air / wz_vapor of one physics group (f:201-202): out[2][GNC]
 void greb_build_wz(float* out, const GrebHostForcing& F, const greb_physics_par& p);
@@ -38,7 +40,8 @@ void greb_build_wz(float* out, const GrebHostForcing& F, const greb_physics_par&
 // initial state of one member (f:190-197): out[GS_COUNT][GNC]
 void greb_build_initial_state(float* out, const GrebHostForcing& F, const GrebMemberConst& mc);
 
-// contiguous row bands per warp, balanced over the four SM sub-partitions (warp w -> SMSP w%4)
-void greb_partition_rows(const int* polar, const int* time2_diff, const int* time2_adv, int* row0, int* nrow);
+// lane group -> latitude row table and helper-warp slots
+int greb_assign_rows(const int* polar, const int* time2_diff, const int* time2_adv, int* row_of_group,
+                     int* hslot_of_row, int* helper_row, int* n_hslots);
 
 bool greb_physics_equal(const greb_physics_par& a, const greb_physics_par& b);

@@ -56,6 +56,67 @@ GDEV vf v_max(vf a, vf b) { return fmaxf(a, b); }
 GDEV vf v_exp(vf a) { return expf(a); }
 GDEV vf v_log(vf a) { return logf(a); }
 GDEV vb v_any_true(vb p) { return __any_sync(0xffffffffu, p); }  // uniform result
+// 4 consecutive floats, 16-byte aligned (LDG.128 / LDS.128 / STG.128 / STS.128)
+GDEV void v_ld4(vf (&o)[4], const float* p, vi idx) {
+  const float4 t = *reinterpret_cast<const float4*>(p + idx);
+  o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
+}
+GDEV void v_ldg4(vf (&o)[4], const float* p, vi idx) {
+  const float4 t = __ldg(reinterpret_cast<const float4*>(p + idx));
+  o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
+}
+GDEV void v_ldgi4(vi (&o)[4], const int* p, vi idx) {
+  const int4 t = __ldg(reinterpret_cast<const int4*>(p + idx));
+  o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
+}
+GDEV void v_st4(float* p, vi idx, vf a, vf b, vf c, vf d) {
+  *reinterpret_cast<float4*>(p + idx) = make_float4(a, b, c, d);
+}
+
+// ---- split-phase CTA barrier (mbarrier): arrive now, wait later --------------------------------
+struct SplitBar { unsigned long long mbar; };
+GDEV void sb_init(SplitBar* b, int count) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(&b->mbar);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
+}
+// one arrival per warp: the warp's shared-memory stores are ordered before it
+GDEV void sb_arrive(const SimtCtx& c, SplitBar* b) {
+  __syncwarp();
+  if (c.lane_u == 0) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(&b->mbar);
+    unsigned long long st;
+    asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 %0, [%1];" : "=l"(st) : "r"(a) : "memory");
+    (void)st;
+  }
+}
+GDEV void sb_wait(const SimtCtx&, SplitBar* b, int phase) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(&b->mbar);
+  unsigned ok;
+  // try_wait with a suspend-time hint: a waiting warp sleeps in hardware instead of burning the
+  // issue slots of the warps it is waiting for
+  do {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2, %3;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(a), "r"((unsigned)(phase & 1)), "r"(2000u)
+        : "memory");
+  } while (!ok);
+}
+// ---- release/acquire flags in shared memory (helper warp -> owner warps) -------------------------
+GDEV void flag_set(const SimtCtx& c, int* f, int v) {
+  __syncwarp();
+  if (c.lane_u == 0) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(f);
+    asm volatile("st.release.cta.shared::cta.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+  }
+}
+GDEV void flag_wait(const SimtCtx&, const int* f, int v) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(f);
+  int cur;
+  do {
+    asm volatile("ld.acquire.cta.shared::cta.s32 %0, [%1];" : "=r"(cur) : "r"(a) : "memory");
+  } while (cur != v);
+}
 
 #else
 // ------------------------------------------------------------------------------------------
@@ -66,6 +127,7 @@ GDEV vb v_any_true(vb p) { return __any_sync(0xffffffffu, p); }  // uniform resu
 #define GUNROLL
 #define GNOUNROLL
 #include <pthread.h>
+#include <sched.h>
 
 #define GW 32
 struct vb {
@@ -119,6 +181,42 @@ GDEV vf v_ldg(const float* p, vi idx) { return v_ld(p, idx); }
 GDEV vi v_ldgi(const int* p, vi idx) { vi r; for (int l = 0; l < GW; ++l) r.v[l] = p[idx.v[l]]; return r; }
 GDEV void v_st(float* p, vi idx, vf v) { for (int l = 0; l < GW; ++l) p[idx.v[l]] = v.v[l]; }
 GDEV bool v_any_true(vb p) { bool a = false; for (int l = 0; l < GW; ++l) a = a || p.v[l]; return a; }
+GDEV void v_ld4(vf (&o)[4], const float* p, vi idx) {
+  for (int q = 0; q < 4; ++q) for (int l = 0; l < GW; ++l) o[q].v[l] = p[idx.v[l] + q];
+}
+GDEV void v_ldg4(vf (&o)[4], const float* p, vi idx) { v_ld4(o, p, idx); }
+GDEV void v_ldgi4(vi (&o)[4], const int* p, vi idx) {
+  for (int q = 0; q < 4; ++q) for (int l = 0; l < GW; ++l) o[q].v[l] = p[idx.v[l] + q];
+}
+GDEV void v_st4(float* p, vi idx, vf a, vf b, vf c, vf d) {
+  for (int l = 0; l < GW; ++l) { p[idx.v[l]] = a.v[l]; p[idx.v[l] + 1] = b.v[l]; p[idx.v[l] + 2] = c.v[l]; p[idx.v[l] + 3] = d.v[l]; }
+}
+// split-phase barrier: counting barrier with generations; every emulated thread group arrives once
+struct EmuBar { pthread_mutex_t mu; pthread_cond_t cv; int count, arrived; long gen; };
+struct SplitBar { EmuBar* p; };  // pointer-sized so that it fits the slot reserved in shared memory
+GDEV void sb_init(SplitBar* b, int count) {
+  b->p = new EmuBar;
+  pthread_mutex_init(&b->p->mu, nullptr); pthread_cond_init(&b->p->cv, nullptr);
+  b->p->count = count; b->p->arrived = 0; b->p->gen = 0;
+}
+GDEV void sb_destroy(SplitBar* b) { delete b->p; }
+GDEV void sb_arrive(const SimtCtx&, SplitBar* b) {
+  EmuBar* e = b->p;
+  pthread_mutex_lock(&e->mu);
+  if (++e->arrived == e->count) { e->arrived = 0; ++e->gen; pthread_cond_broadcast(&e->cv); }
+  pthread_mutex_unlock(&e->mu);
+}
+// waits until phase number `phase` (0-based) is complete, i.e. phase+1 generations have finished
+GDEV void sb_wait(const SimtCtx&, SplitBar* b, int phase) {
+  EmuBar* e = b->p;
+  pthread_mutex_lock(&e->mu);
+  while (e->gen < (long)phase + 1) pthread_cond_wait(&e->cv, &e->mu);
+  pthread_mutex_unlock(&e->mu);
+}
+GDEV void flag_set(const SimtCtx&, int* f, int v) { __atomic_store_n(f, v, __ATOMIC_RELEASE); }
+GDEV void flag_wait(const SimtCtx&, const int* f, int v) {
+  while (__atomic_load_n(f, __ATOMIC_ACQUIRE) != v) sched_yield();
+}
 
 // operators so that expression code reads the same in both builds
 GDEV vf operator+(vf a, vf b) { return v_add(a, b); }

@@ -7,9 +7,25 @@
 #define GNT 730         // steps per year (nstep_yr, :41)
 #define GSUB 24         // circulation sub-steps per step: nint(43200/1800) (:543)
 
-#define GREB_NWARP 12   // warps per member CTA
-#define GREB_MAXR 5     // max latitude rows owned by one warp
+// CTA shape: 12 "main" warps, each lane group of 8 lanes owns one latitude row (12 consecutive
+// longitudes per lane, 4 rows per warp), plus GREB_NHELP helper warps that run the polar
+// sub-sub-steps of the rows whose diffusion needs more than one (time2_diff > 1, f:652-717).
+#define GREB_NMAIN 12
+#define GREB_NHELP 2
+#define GREB_NWARP (GREB_NMAIN + GREB_NHELP)
 #define GREB_NTHREADS (GREB_NWARP * 32)
+#define GREB_CPT 12     // cells per thread (96 / 8)
+#define GREB_MAXH 4     // max helper-owned rows (2 per helper warp)
+
+// shared memory layout of a member CTA, in floats
+#define GSM_HB 0                        // [2][GNC]   double-buffered copy of the circulating field
+#define GSM_STASH (2 * GNC)             // [2][GNC]   tendA, tq between the column phase and the circulations
+#define GSM_SYNC (4 * GNC)              // SplitBar (32 floats reserved)
+// per-thread private constants of the y-direction part, kept out of the register file:
+// [PRIV_*][chunk 0..2][main thread 0..383][4]  -> consecutive threads read consecutive 16 bytes
+#define GSM_PRIV (GSM_SYNC + 32)
+enum { PRIV_V = 0, PRIV_WM1, PRIV_WP1, PRIV_WFY, PRIV_COUNT };
+#define GSM_FLOATS (GSM_PRIV + PRIV_COUNT * 3 * GREB_NMAIN * 32 * 4)
 
 // per-step shared forcing record: forc[ityr][GF_*][GNC]
 enum { GF_U = 0, GF_V, GF_CLD, GF_DTRAD, GF_SWET, GF_ABSWIND, GF_MLD, GF_DMLD, GF_COUNT };
@@ -34,10 +50,15 @@ struct GrebMemberConst {
   float ccy_diff, ccy_adv;
   float ccx_diff[GY], ccx_adv[GY], ccx2_diff[GY], ccx2_adv[GY];
   int polar[GY], time2_diff[GY], time2_adv[GY];
-  // row ownership: warp w owns rows [row0[w], row0[w]+nrow[w])
-  int row0[GREB_NWARP], nrow[GREB_NWARP];
+  // row ownership: main lane group g = 4*warp + (lane>>3) owns latitude row row_of_group[g]
+  int row_of_group[GY];
+  // rows whose polar diffusion needs several sub-sub-steps go to the helper warps:
+  // hslot_of_row[k] = slot or -1; helper warp h serves slots h, h+GREB_NHELP, ...
+  int hslot_of_row[GY];
+  int helper_row[GREB_MAXH];
+  int n_hslots;
   int group;  // physics group (shares wz fields and flux corrections)
-  int pad_[3];
+  int pad_[2];
 };
 
 struct GrebKernelArgs {

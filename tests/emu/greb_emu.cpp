@@ -9,6 +9,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <stdint.h>
+
 #include <vector>
 
 #include "greb_core.h"
@@ -33,37 +35,59 @@ struct WarpTask {
   int n_idx;
 };
 
+#define EMU_UNITS (GY + GREB_NHELP)  // 48 row groups (8 lanes each) + the helper warps
+
 void* warp_main(void* p) {
   WarpTask* t = (WarpTask*)p;
   if (t->ka) {
     member_run(t->ctx, *t->ka, *t->mc, 0);
   } else {
     const GrebCirculationArgs& a = *t->ca;
-    const WarpGeom g = warp_geom(t->ctx, *t->mc);
-    CircTile tile;
-    circ_load_uv(tile, g, a.uv, a.uv + GNC);
-    circ_load_wz(tile, g, a.wz + (size_t)t->n_idx * GNC);
-    circ_load_field(tile, g, a.X_in + (size_t)t->n_idx * GNC);
-    circulation_run(t->ctx, tile, g, *t->mc, t->ctx.smem);
-    for (int r = 0; r < g.nr; ++r)
-      for (int c = 0; c < 3; ++c) {
-        const vi idx = (g.k0 + r) * GX + g.col + c;
-        v_st(a.dX + (size_t)t->n_idx * GNC, idx, tile.Y[r + 2][c] - v_ld(a.X_in + (size_t)t->n_idx * GNC, idx));
+    const GrebMemberConst& mc = *t->mc;
+    float* smem = t->ctx.smem;
+    SyncState ss;
+    ss.bar = reinterpret_cast<SplitBar*>(smem + GSM_SYNC);
+    ss.hb = smem + GSM_HB;
+    ss.smem = smem;
+    ss.phase = 0;
+    const size_t off = (size_t)t->n_idx * GNC;
+    if (!ctx_is_helper(t->ctx)) {
+      const RowGeom g = row_geom(t->ctx, mc);
+      Tile tile;
+      tile_load_uv(tile, g, a.uv, a.uv + GNC, smem);
+      tile_load_wz(tile, g, a.wz + off, smem);
+      tile_load_field(tile, g, a.X_in + off);
+      circulation_main(t->ctx, tile, g, mc, ss);
+      for (int c = 0; c < GREB_CPT; ++c) {
+        const vi idx = g.k * GX + g.col + c;
+        v_st(a.dX + off, idx, tile.T[c] - v_ld(a.X_in + off, idx));
       }
+    } else {
+      const HelperGeom hg = helper_geom(t->ctx, mc);
+      HelperRow hr[GREB_HROWS];
+      helper_load_uv(hr, hg, a.uv, a.uv + GNC);
+      helper_load_wz(hr, hg, a.wz + off);
+      circulation_helper(t->ctx, hr, hg, mc, a.X_in + off, ss);
+    }
   }
   return nullptr;
 }
 
 void run_cta(const GrebKernelArgs* ka, const GrebCirculationArgs* ca, const GrebMemberConst* mc, int n_idx) {
-  std::vector<float> smem(4 * GNC, 0.f);
+  std::vector<float> smem(GSM_FLOATS + 64, 0.f);
+  // SplitBar needs pointer alignment
+  float* base = smem.data();
+  while (((uintptr_t)(base + GSM_SYNC)) % 16) ++base;
+  sb_init(reinterpret_cast<SplitBar*>(base + GSM_SYNC), EMU_UNITS);
+  static_assert(sizeof(SplitBar) <= 16 * sizeof(float), "SplitBar fits its shared-memory slot");
   pthread_barrier_t bar;
-  pthread_barrier_init(&bar, nullptr, GREB_NWARP);
-  WarpTask tasks[GREB_NWARP];
-  pthread_t th[GREB_NWARP];
-  for (int w = 0; w < GREB_NWARP; ++w) {
+  pthread_barrier_init(&bar, nullptr, EMU_UNITS);
+  std::vector<WarpTask> tasks(EMU_UNITS);
+  std::vector<pthread_t> th(EMU_UNITS);
+  for (int w = 0; w < EMU_UNITS; ++w) {
     tasks[w].ctx.warp = w;
     for (int l = 0; l < 32; ++l) tasks[w].ctx.lane_v.v[l] = l;
-    tasks[w].ctx.smem = smem.data();
+    tasks[w].ctx.smem = base;
     tasks[w].ctx.bar = &bar;
     tasks[w].ka = ka;
     tasks[w].ca = ca;
@@ -71,8 +95,9 @@ void run_cta(const GrebKernelArgs* ka, const GrebCirculationArgs* ca, const Greb
     tasks[w].n_idx = n_idx;
     pthread_create(&th[w], nullptr, warp_main, &tasks[w]);
   }
-  for (int w = 0; w < GREB_NWARP; ++w) pthread_join(th[w], nullptr);
+  for (int w = 0; w < EMU_UNITS; ++w) pthread_join(th[w], nullptr);
   pthread_barrier_destroy(&bar);
+  sb_destroy(reinterpret_cast<SplitBar*>(base + GSM_SYNC));
 }
 
 }  // namespace
@@ -97,11 +122,13 @@ int emu_circulation(const greb_physics_par* p, const float* u, const float* v, c
   return 0;
 }
 
-void emu_partition(const greb_physics_par* p, int* row0, int* nrow) {
+// row_of_group[48], hslot_of_row[48]; returns greb_build_member_const's status
+int emu_row_tables(const greb_physics_par* p, int* row_of_group, int* hslot_of_row) {
   GrebMemberConst mc;
-  greb_build_member_const(mc, *p, 0);
-  memcpy(row0, mc.row0, sizeof mc.row0);
-  memcpy(nrow, mc.nrow, sizeof mc.nrow);
+  const int rc = greb_build_member_const(mc, *p, 0);
+  memcpy(row_of_group, mc.row_of_group, sizeof mc.row_of_group);
+  memcpy(hslot_of_row, mc.hslot_of_row, sizeof mc.hslot_of_row);
+  return rc;
 }
 
 void* emu_create(const float* z_topo, const float* glacier, const float* sw_solar, const float* tclim,

@@ -33,7 +33,7 @@ def lib():
         build()
         L = C.CDLL(LIB)
         L.emu_circulation.argtypes = [C.c_void_p, fp, fp, fp, fp, fp]
-        L.emu_partition.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.emu_row_tables.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.emu_create.restype = C.c_void_p
         L.emu_create.argtypes = [fp] * 10 + [C.c_void_p, fp, C.c_int]
         L.emu_destroy.argtypes = [C.c_void_p]
@@ -62,11 +62,12 @@ def circulation(phys, u, v, X, wz):
     return out
 
 
-def partition(phys):
-    r0 = (C.c_int * 12)()
-    nr = (C.c_int * 12)()
-    lib().emu_partition(C.byref(phys), r0, nr)
-    return list(r0), list(nr)
+def row_tables(phys):
+    """(status, row_of_group[48], hslot_of_row[48]) of the host-side row assignment"""
+    rg = (C.c_int * 48)()
+    hs = (C.c_int * 48)()
+    rc = lib().emu_row_tables(C.byref(phys), rg, hs)
+    return rc, list(rg), list(hs)
 
 
 class Emu:

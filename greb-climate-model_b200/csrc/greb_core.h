@@ -6,7 +6,7 @@
 //     (the hot loop is ~10 KB of SASS instead of an unrolled per-row body per warp).  The periodic
 //     longitude wrap is a rotation inside the 8-lane group (SHFL); the rows above and below come from
 //     a double-buffered shared-memory copy of the field (LDS.128), published once per sub-step.
-//   * 4 helper warps (two pairs alternating sub-steps) own the circulation of the two pole rows and of any other row whose polar
+//   * 2 helper warps own the circulation of the two pole rows and of any other row whose polar
 //     x-diffusion needs several sub-sub-steps (time2_diff > 1: 8 dependent iterations on the pole
 //     rows at the default kappa): a whole row per warp at 3 cells per lane, so that serial chain
 //     runs inside one warp, in parallel with the other 46 rows, instead of stalling a main warp.
@@ -364,7 +364,7 @@ GDEV void xdiff_bracket3(vf (&S)[3], const XRow& x) {
   S[2] = v_fma(4.0f, B2, v_fma(4.0f, A1, 10.0f * G2)) + A0 + B3;
 }
 
-#define GREB_HROWS (GREB_MAXH / GREB_NPAIR)  // rows per helper pair
+#define GREB_HROWS (GREB_MAXH / GREB_NHELP)  // rows per helper warp
 
 struct HelperRow {
   vf T[3];                                   // the circulating field
@@ -375,8 +375,7 @@ struct HelperRow {
 };
 
 struct HelperGeom {
-  int parity;                  // this warp works on the sub-steps tt with (tt & 1) == parity
-  int n;                       // rows served by this helper pair
+  int n;                       // rows served by this helper warp
   int k[GREB_HROWS];
   vi col, lane_l, lane_r;
   vb is_bug;                   // lane 31 owns longitude 93 as its first cell (f:881)
@@ -390,10 +389,9 @@ GDEV HelperGeom helper_geom(const SimtCtx& ctx, const GrebMemberConst& mc) {
   g.lane_r = (lane + 1) & 31;
   g.is_bug = (lane == 31);
   g.n = 0;
-  g.parity = ctx_helper_index(ctx) & 1;
   GUNROLL
   for (int i = 0; i < GREB_HROWS; ++i) {
-    const int s = (ctx_helper_index(ctx) >> 1) + i * GREB_NPAIR;
+    const int s = ctx_helper_index(ctx) + i * GREB_NHELP;
     g.k[i] = (s < mc.n_hslots) ? mc.helper_row[s] : 0;
     if (s < mc.n_hslots) g.n = i + 1;
   }
@@ -555,36 +553,32 @@ GDEV void circulation_main(const SimtCtx& ctx, Tile& t, const RowGeom& g, const 
 
 GDEV void circulation_helper(const SimtCtx& ctx, HelperRow (&hr)[GREB_HROWS], const HelperGeom& g,
                              const GrebMemberConst& mc, const float* X, SyncState& ss) {
-  // the two warps of a pair take turns: the even one publishes the initial rows and runs the even
-  // sub-steps, the odd one the odd sub-steps; the rows travel between them through the field buffer
-  if (g.parity == 0) {
-    GUNROLL
-    for (int i = 0; i < GREB_HROWS; ++i)
-      if (i < g.n) {
-        GUNROLL
-        for (int c = 0; c < 3; ++c)
-          v_st(ss.hb + (ss.phase & 1) * GNC, g.k[i] * GX + g.col + c, v_ld(X, g.k[i] * GX + g.col + c));
+  GUNROLL
+  for (int i = 0; i < GREB_HROWS; ++i)
+    if (i < g.n) {
+      GUNROLL
+      for (int c = 0; c < 3; ++c) {
+        hr[i].T[c] = v_ld(X, g.k[i] * GX + g.col + c);
+        v_st(ss.hb + (ss.phase & 1) * GNC, g.k[i] * GX + g.col + c, hr[i].T[c]);
       }
-  }
+    }
   sb_arrive(ctx, ss.bar);
   GNOUNROLL
   for (int tt = 0; tt < GSUB; ++tt) {
+    GUNROLL
+    for (int i = 0; i < GREB_HROWS; ++i)
+      if (i < g.n) helper_x(hr[i], g, mc, g.k[i]);
     sb_wait(ctx, ss.bar, ss.phase);
     const float* buf = ss.hb + (ss.phase & 1) * GNC;
     ss.phase++;
-    if ((tt & 1) == g.parity) {
-      float* nxt = ss.hb + (ss.phase & 1) * GNC;
-      GUNROLL
-      for (int i = 0; i < GREB_HROWS; ++i)
-        if (i < g.n) {
-          GUNROLL
-          for (int c = 0; c < 3; ++c) hr[i].T[c] = v_ld(buf, g.k[i] * GX + g.col + c);
-          helper_x(hr[i], g, mc, g.k[i]);
-          helper_y(hr[i], g, mc, g.k[i], buf);
-          GUNROLL
-          for (int c = 0; c < 3; ++c) v_st(nxt, g.k[i] * GX + g.col + c, hr[i].T[c]);
-        }
-    }
+    float* nxt = ss.hb + (ss.phase & 1) * GNC;
+    GUNROLL
+    for (int i = 0; i < GREB_HROWS; ++i)
+      if (i < g.n) {
+        helper_y(hr[i], g, mc, g.k[i], buf);
+        GUNROLL
+        for (int c = 0; c < 3; ++c) v_st(nxt, g.k[i] * GX + g.col + c, hr[i].T[c]);
+      }
     sb_arrive(ctx, ss.bar);
   }
   sb_wait(ctx, ss.bar, ss.phase);

@@ -8,17 +8,14 @@
 #define GSUB 24         // circulation sub-steps per step: nint(43200/1800) (:543)
 
 // CTA shape: 12 "main" warps, each lane group of 8 lanes owns one latitude row (12 consecutive
-// longitudes per lane, 4 rows per warp), plus 4 helper warps that circulate the pole rows and any
-// other row whose polar diffusion needs several sub-sub-steps (time2_diff > 1, f:652-717).  The
-// helpers work in pairs that alternate sub-steps, so each of the four SM sub-partitions carries
-// three main warps and one half-loaded helper warp.
+// longitudes per lane, 4 rows per warp), plus GREB_NHELP helper warps that run the polar
+// sub-sub-steps of the rows whose diffusion needs more than one (time2_diff > 1, f:652-717).
 #define GREB_NMAIN 12
-#define GREB_NHELP 4
-#define GREB_NPAIR (GREB_NHELP / 2)
+#define GREB_NHELP 2
 #define GREB_NWARP (GREB_NMAIN + GREB_NHELP)
 #define GREB_NTHREADS (GREB_NWARP * 32)
 #define GREB_CPT 12     // cells per thread (96 / 8)
-#define GREB_MAXH 4     // max helper-owned rows (2 per helper pair)
+#define GREB_MAXH 4     // max helper-owned rows (2 per helper warp)
 
 // shared memory layout of a member CTA, in floats
 #define GSM_HB 0                        // [2][GNC]   double-buffered copy of the circulating field

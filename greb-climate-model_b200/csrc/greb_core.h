@@ -888,12 +888,21 @@ GDEV void member_run_main(const SimtCtx& ctx, const GrebKernelArgs& a, const Gre
       tile_load_wz(t, g, wzg + fld * GNC, smem);
       tile_load_field(t, g, st + (fld == 0 ? GS_TA : GS_Q) * GNC);
       circulation_main(ctx, t, g, mc, ss);
-      if (fld == 0) sb_wait(ctx, ss.colbar, it - a.it0);  // phase A of this step is complete (stash, accumulators)
-      GUNROLL
-      for (int q = 0; q < 3; ++q) {
-        if (fld == 0) column_phase_b(a, member, si, g.k * GX + g.col + 4 * q, &t.T[4 * q], stash);
-        else column_phase_c(a, mc, member, si, g.k * GX + g.col + 4 * q, &t.T[4 * q], stash);
+      if (fld == 0) {
+        // park the circulated air temperature in the thread's private slot: phases B and C both run
+        // after the second circulation, so the column warps have two circulations to finish phase A
+        GUNROLL
+        for (int q = 0; q < 3; ++q)
+          v_st4(priv_ptr(smem, PRIV_XTA, q), g.tid4, t.T[4 * q], t.T[4 * q + 1], t.T[4 * q + 2], t.T[4 * q + 3]);
       }
+    }
+    sb_wait(ctx, ss.colbar, it - a.it0);  // phase A of this step is complete (stash, accumulators)
+    GUNROLL
+    for (int q = 0; q < 3; ++q) {
+      vf xta[4];
+      v_ld4(xta, priv_ptr(smem, PRIV_XTA, q), g.tid4);
+      column_phase_b(a, member, si, g.k * GX + g.col + 4 * q, xta, stash);
+      column_phase_c(a, mc, member, si, g.k * GX + g.col + 4 * q, &t.T[4 * q], stash);
     }
 
     // ---- output (f:975-985)

@@ -25,7 +25,7 @@
 // per-thread private constants of the y-direction part, kept out of the register file:
 // [PRIV_*][chunk 0..2][main thread 0..383][4]  -> consecutive threads read consecutive 16 bytes
 #define GSM_PRIV (GSM_SYNC + 32)
-enum { PRIV_V = 0, PRIV_WM1, PRIV_WP1, PRIV_WFY, PRIV_COUNT };
+enum { PRIV_V = 0, PRIV_WM1, PRIV_WP1, PRIV_WFY, PRIV_XTA, PRIV_COUNT };  // XTA: circulated air temperature
 #define GSM_FLOATS (GSM_PRIV + PRIV_COUNT * 3 * GREB_NMAIN * 32 * 4)
 
 // per-step shared forcing record: forc[ityr][GF_*][GNC]

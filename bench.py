@@ -200,7 +200,7 @@ def main():
     import torch
     import torch.distributed as dist
     import greb_b200
-    from greb_b200 import flops as fm, synth
+    from greb_b200 import flops as fm, sharding, synth
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the B200 path has no CPU fallback")
@@ -217,8 +217,10 @@ def main():
     ens = greb_b200.Ensemble(M, device=local)
     ens.set_forcing(forcing)
     flops_year = 0.0
+    first, last = sharding.shard_range(M * world, world, rank)   # weak scaling: M members per rank
+    assert last - first == M
     for m in range(M):
-        p, co2 = member_physics(rank * M + m, greb_b200.default_physics)
+        p, co2 = member_physics(first + m, greb_b200.default_physics)
         if args.shared_physics:
             p = greb_b200.default_physics()
         flops_year += fm.flops_per_member_year(p.pi, p.kappa)

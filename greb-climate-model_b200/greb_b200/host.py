@@ -1,0 +1,348 @@
+"""Host front-end of the reference, restated for batched runs.
+
+What `PROGRAM greb_run` does for ONE member (reference src/greb.f90:996-1098) this module does
+for a list of namelists at once: read the four namelist groups in the reference's order, pad
+`co2_ppm` (f:1047-1061), build `output_file // '_' // ens_id` (f:1063-1068), read the ten
+direct-access input files (f:1018-1027, 1073-1085), run all members as ONE ensemble on the GPU
+through the C ABI, and write each member's `output/scenario[_ens_id]` byte-compatible with the
+reference (5 records per month, f:978-982) plus the yearly console line (f:954).
+
+`read_greb` is a port of the reference's reader R/functions.R:34-81, the normative description
+of the output layout.
+
+Nothing here computes physics: the stepping runs on the B200 (`Ensemble`); without the CUDA
+library / a GPU `run_namelists` raises.
+"""
+from __future__ import annotations
+
+import dataclasses
+import os
+import re
+from typing import Dict, List, Sequence
+
+import numpy as np
+
+from . import lib as _lib
+from . import synth
+
+XD, YD, NT = 96, 48, 730
+VARNAMES = ("tsurf", "tair", "tocean", "vapor", "albedo")   # record order of f:978-982 / R/functions.R:23-32
+
+
+# ------------------------------------------------------------------------------------------------
+# namelists
+# ------------------------------------------------------------------------------------------------
+class NamelistError(ValueError):
+    pass
+
+
+def _strip_comment(line: str) -> str:
+    out, q = [], None
+    for ch in line:
+        if q:
+            out.append(ch)
+            if ch == q:
+                q = None
+        elif ch in "'\"":
+            q = ch
+            out.append(ch)
+        elif ch == "!":
+            break
+        else:
+            out.append(ch)
+    return "".join(out)
+
+
+def _scalar(tok: str):
+    t = tok.strip()
+    if not t:
+        raise NamelistError("empty value")
+    if t[0] in "'\"":
+        if len(t) < 2 or t[-1] != t[0]:
+            raise NamelistError(f"unterminated string {t!r}")
+        return t[1:-1]
+    tl = t.lower()
+    if tl in (".true.", "t", ".t."):
+        return True
+    if tl in (".false.", "f", ".f."):
+        return False
+    if re.fullmatch(r"[+-]?\d+", t):
+        return int(t)
+    try:
+        return float(tl.replace("d", "e"))
+    except ValueError:
+        raise NamelistError(f"cannot parse value {t!r}") from None
+
+
+def _values(text: str):
+    text = text.strip().rstrip(",").strip()
+    if text.startswith("(/") and text.endswith("/)"):
+        text = text[2:-2]
+    parts, cur, q = [], [], None
+    for ch in text:
+        if q:
+            cur.append(ch)
+            if ch == q:
+                q = None
+        elif ch in "'\"":
+            q = ch
+            cur.append(ch)
+        elif ch == "," or (ch.isspace() and cur and "".join(cur).strip()):
+            if "".join(cur).strip():
+                parts.append("".join(cur))
+            cur = []
+        else:
+            cur.append(ch)
+    if "".join(cur).strip():
+        parts.append("".join(cur))
+    vals = []
+    for p in parts:
+        m = re.fullmatch(r"\s*(\d+)\*(.+)", p)          # repeat count r*c
+        if m:
+            vals.extend([_scalar(m.group(2))] * int(m.group(1)))
+        else:
+            vals.append(_scalar(p))
+    return vals
+
+
+def parse_namelist(text: str) -> Dict[str, Dict[str, list]]:
+    """{group: {name: [values]}} — group and variable names lower-cased, `! comments`, `&G ... /`
+    (or `&end`), `a = 1, 2, 3`, `(/ .. /)`, repeat counts, quoted strings, empty groups."""
+    body = "\n".join(_strip_comment(ln) for ln in text.splitlines())
+    groups: Dict[str, Dict[str, list]] = {}
+    pos = 0
+    while True:
+        m = re.search(r"&\s*([A-Za-z_]\w*)", body[pos:])
+        if not m:
+            break
+        name = m.group(1).lower()
+        start = pos + m.end()
+        end = None
+        q = None
+        for i in range(start, len(body)):
+            ch = body[i]
+            if q:
+                if ch == q:
+                    q = None
+            elif ch in "'\"":
+                q = ch
+            elif ch == "/" and not (body[i - 1:i + 1] == "(/" or body[i:i + 2] == "/)"):
+                end = i
+                break
+            elif body[i:i + 4].lower() == "&end":
+                end = i
+                break
+        if end is None:
+            raise NamelistError(f"namelist group &{name} is not terminated by '/'")
+        content = body[start:end]
+        items: Dict[str, list] = {}
+        # split "name = values" pairs: a new pair starts at an identifier followed by '='
+        pairs = list(re.finditer(r"([A-Za-z_]\w*)\s*(\(\s*\d+\s*\))?\s*=", content))
+        for j, pm in enumerate(pairs):
+            v_end = pairs[j + 1].start() if j + 1 < len(pairs) else len(content)
+            items[pm.group(1).lower()] = _values(content[pm.end():v_end])
+        if name in groups:
+            raise NamelistError(f"namelist group &{name} appears twice")
+        groups[name] = items
+        pos = end + 1
+    return groups
+
+
+@dataclasses.dataclass
+class RunConfig:
+    """One `./greb <namelist>` invocation (f:1042-1068)."""
+    physics: "_lib.Physics"
+    time_flux: int = 0
+    time_scnr: int = 0
+    year0: int = 1940
+    ipx: int = 1
+    ipy: int = 1
+    output_file: str = "output/scenario"
+    ens_id: str = ""
+    co2_ppm: np.ndarray = dataclasses.field(default_factory=lambda: np.zeros(0, dtype=np.float32))
+
+    @property
+    def output_file_full(self) -> str:                                  # f:1063-1068
+        return self.output_file if not self.ens_id.strip() else f"{self.output_file.strip()}_{self.ens_id.strip()}"
+
+
+_PHYS = {n.lower(): n for n in _lib.PHYS_FIELDS}
+
+
+def pad_co2(given: Sequence[float], n_years: int) -> np.ndarray:
+    """f:1047-1061: allocate(time_scnr) = -1; first < 0 -> 680; the tail repeats the last value."""
+    co2 = np.full(n_years, -1.0, dtype=np.float32)
+    g = np.asarray(list(given), dtype=np.float32)[:n_years]
+    co2[:len(g)] = g
+    if n_years > 0 and co2[0] == -1:
+        co2[0] = 680.0
+    for i in range(1, n_years):
+        if co2[i] < 0:
+            co2[i:] = co2[i - 1]
+            break
+    return co2
+
+
+def config_from_namelist(text: str, defaults: "_lib.Physics | None" = None) -> RunConfig:
+    """The four groups of greb.f90 (`physics_par`, `numerics_par`, `diagnostics_par`, `co2_par`); a
+    missing group keeps its defaults (the reference requires all four to be present, f:1042-1050)."""
+    g = parse_namelist(text)
+    known = {"physics_par", "numerics_par", "diagnostics_par", "co2_par"}
+    extra = set(g) - known
+    if extra:
+        raise NamelistError(f"unknown namelist group(s): {sorted(extra)}")
+    p = defaults.copy() if defaults is not None else _default_physics_struct()
+    for k, v in g.get("physics_par", {}).items():
+        if k == "p_emi":
+            if len(v) > 10:
+                raise NamelistError("p_emi has 10 elements")
+            for i, x in enumerate(v):
+                p.p_emi[i] = float(x)
+        elif k in _PHYS:
+            setattr(p, _PHYS[k], float(v[0]))
+        else:
+            raise NamelistError(f"physics_par: unknown variable {k}")
+    cfg = RunConfig(physics=p)
+    for k, v in g.get("numerics_par", {}).items():
+        if k not in ("ipx", "ipy", "time_flux", "time_scnr", "year0"):
+            raise NamelistError(f"numerics_par: unknown variable {k}")
+        setattr(cfg, k, int(v[0]))
+    for k, v in g.get("diagnostics_par", {}).items():
+        if k not in ("output_file", "ens_id"):
+            raise NamelistError(f"diagnostics_par: unknown variable {k}")
+        setattr(cfg, k, str(v[0]))
+    given = []
+    for k, v in g.get("co2_par", {}).items():
+        if k == "co2_flux":
+            p.co2_flux = float(v[0])
+        elif k == "co2_ppm":
+            given = [float(x) for x in v]
+        else:
+            raise NamelistError(f"co2_par: unknown variable {k}")
+    if len(given) > max(cfg.time_scnr, 0):
+        # gfortran aborts when more values than allocated elements are supplied
+        raise NamelistError(f"co2_ppm has {len(given)} values but time_scnr = {cfg.time_scnr}")
+    cfg.co2_ppm = pad_co2(given, cfg.time_scnr)
+    return cfg
+
+
+def _default_physics_struct() -> "_lib.Physics":
+    """Reference defaults f:68-104 without touching the CUDA library (so that namelists parse on any
+    host); tests/test_host_formats.py checks them against greb_b200_physics_defaults."""
+    p = _lib.Physics()
+    f32 = np.float32
+    vals = dict(pi=3.1416, sig=5.6704e-8, rho_ocean=999.1, rho_land=2600., rho_air=1.2, cp_ocean=4186.,
+                cp_land=926.222, cp_air=1005., eps=1., d_ocean=50., d_land=2., d_air=5000., ct_sens=22.5,
+                da_ice=0.25, a_no_ice=0.1, a_cloud=0.35, Tl_ice1=float(f32(273.15) - f32(10.)), Tl_ice2=273.15,
+                To_ice1=float(f32(273.15) - f32(7.)), To_ice2=float(f32(273.15) - f32(1.7)), co_turb=5.0, kappa=8e5,
+                ce=2e-3, cq_latent=2.257e6, cq_rain=float(f32(f32(-0.1) / f32(24.)) / f32(3600.)), z_air=8400.,
+                z_vapor=5000., r_qviwv=2.6736e3)
+    for k, v in vals.items():
+        setattr(p, k, v)
+    for i, x in enumerate((9.0721, 106.7252, 61.5562, 0.0179, 0.0028, 0.0570, 0.3462, 2.3406, 0.7032, 1.0662)):
+        p.p_emi[i] = x
+    p.co2_flux = 298.
+    return p
+
+
+# ------------------------------------------------------------------------------------------------
+# files
+# ------------------------------------------------------------------------------------------------
+def read_inputs(directory: str = "input") -> "synth.Forcing":
+    """The ten direct-access files of f:1018-1027 (RECL = 4*xdim*ydim bytes, little-endian fp32)."""
+    missing = [n for n in synth.INPUT_FILES if not os.path.exists(os.path.join(directory, n))]
+    if missing:
+        raise FileNotFoundError(f"{directory}: missing input file(s) {missing}")
+    return synth.Forcing.read(directory)
+
+
+def write_output(path: str, monthly: np.ndarray) -> None:
+    """`monthly` [years][12][5][48][96] -> the reference's record stream (f:978-982).  Like the
+    reference (opened without status='replace', f:174) a longer existing file is not truncated."""
+    a = np.ascontiguousarray(monthly, dtype="<f4")
+    if a.shape[-3:] != (5, YD, XD):
+        raise ValueError("monthly must end in [5][48][96]")
+    os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+    mode = "r+b" if os.path.exists(path) else "wb"
+    with open(path, mode) as fh:
+        fh.seek(0)
+        fh.write(a.tobytes())
+
+
+def read_greb(file: str, tstamps=None, varname: Sequence[str] = VARNAMES, ivar: Sequence[int] | None = None,
+              nvar: int | None = None, nlon: int = XD, nlat: int = YD, nbyte: int = 4):
+    """Port of R/functions.R:34-81.  Returns dict(time, variable, lon, lat, value) where value has
+    shape [ntime][len(ivar)][nlat][nlon] (lon fastest in the file, R/functions.R:45-51)."""
+    varname = list(varname)
+    ivar = list(range(1, len(varname) + 1)) if ivar is None else list(ivar)
+    nvar = max(ivar) if nvar is None else nvar
+    if len(ivar) != len(varname):
+        raise ValueError("ivar and varname must have the same length")
+    size = os.path.getsize(file)
+    ngrid = nlon * nlat
+    ntime, rem = divmod(size, ngrid * nvar * nbyte)
+    if rem != 0:                                                    # R/functions.R:41
+        raise ValueError(f"{file}: size {size} is not a multiple of nlon*nlat*nvar*nbyte = {ngrid * nvar * nbyte}")
+    tstamps = list(range(1, ntime + 1)) if tstamps is None else list(tstamps)
+    if len(tstamps) != ntime:
+        raise ValueError("length(tstamps) != ntime")
+    dlon, dlat = 360.0 / nlon, 180.0 / nlat
+    lon = dlon / 2 + dlon * np.arange(nlon)                         # 1.875 ... 358.125
+    lat = -90.0 + dlat / 2 + dlat * np.arange(nlat)                 # -88.125 ... 88.125
+    data = np.fromfile(file, dtype="<f4").reshape(ntime, nvar, nlat, nlon)
+    value = data[:, [i - 1 for i in ivar]]
+    return {"time": tstamps, "variable": varname, "lon": lon, "lat": lat, "value": value}
+
+
+def console_line(year: float, co2: float, gmean: float, point: float) -> str:
+    """The yearly line of f:954 (list-directed `print *` of four reals)."""
+    return f"   {year:12.6f}   {co2:12.6f}   {gmean:12.8f}   {point:12.8f}"
+
+
+# ------------------------------------------------------------------------------------------------
+# batched driver: N namelists -> one ensemble on the GPU
+# ------------------------------------------------------------------------------------------------
+def run_namelists(namelists: Sequence[str], input_dir: str = "input", workdir: str = ".", device: int = 0,
+                  write_files: bool = True, verbose: bool = False):
+    """`./greb nml_1`, `./greb nml_2`, ... as ONE batch.  All members must share `time_flux` and
+    `time_scnr` (one launch advances every member by the same number of steps).  Returns a list of
+    dicts(config, monthly [years][12][5][48][96], gmean [years], point [years], lines)."""
+    cfgs = []
+    for n in namelists:
+        with open(n) as fh:
+            cfgs.append(config_from_namelist(fh.read()))
+    if not cfgs:
+        return []
+    tf, ts = cfgs[0].time_flux, cfgs[0].time_scnr
+    if any(c.time_flux != tf or c.time_scnr != ts for c in cfgs):
+        raise ValueError("run_namelists: all members of a batch must share time_flux and time_scnr")
+    forcing = read_inputs(input_dir)
+    ens = _lib.Ensemble(len(cfgs), device=device)
+    try:
+        ens.set_forcing(forcing)
+        for m, c in enumerate(cfgs):
+            ens.set_member(m, c.physics, c.co2_ppm if ts > 0 else [680.0], year0=c.year0)
+        ens.init()
+        ens.spinup(tf)                                              # f:221
+        ens.reset_scenario()                                        # f:226-227
+        results = [dict(config=c, monthly=np.zeros((ts, 12, 5, YD, XD), np.float32), gmean=np.zeros(ts, np.float32),
+                        point=np.zeros(ts, np.float32), lines=[]) for c in cfgs]
+        for y in range(ts):                                         # one simulated year per launch
+            out, gm, _ = ens.run(1)
+            for m, (c, r) in enumerate(zip(cfgs, results)):
+                r["monthly"][y] = out[m, 0]
+                r["gmean"][y] = gm[m, 0]
+                # f:954 prints tsmn(ipx,ipy)-273.15, the annual mean of Tsurf at the diagnostic point; the
+                # ABI returns monthly means, so the point value is their day-weighted mean (not bit-exact)
+                w = np.array([31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31], dtype=np.float64)
+                ts_pt = out[m, 0, :, 0, c.ipy - 1, c.ipx - 1].astype(np.float64)
+                r["point"][y] = np.float32((ts_pt * w).sum() / w.sum() - 273.15)
+                r["lines"].append(console_line(c.year0 + y, float(c.co2_ppm[y]), float(gm[m, 0]), float(r["point"][y])))
+                if verbose:
+                    print(r["lines"][-1])
+        if write_files:
+            for r in results:
+                write_output(os.path.join(workdir, r["config"].output_file_full), r["monthly"])
+        return results
+    finally:
+        ens.close()

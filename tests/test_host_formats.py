@@ -1,0 +1,113 @@
+"""Host front-end formats: namelists, co2 padding, ens_id naming, the output
+record stream and the read_greb port.  CPU only."""
+import os
+
+import numpy as np
+import pytest
+
+from greb_b200 import host, lib
+
+# the reference's default namelist (reference `namelist:1-14`) — configuration text, restated
+REFERENCE_NAMELIST = """
+&PHYSICS_PAR
+/
+&NUMERICS_PAR
+ipx = 95 ! diagnostic output point, x-coord
+ipy = 38 ! diagnostic output point, y-coord
+time_flux = 3  ! length of flux corrections run [yrs]
+time_scnr = 50 ! length of scenariorun [yrs]
+/
+&DIAGNOSTICS_PAR
+output_file = "output/scenario"
+/
+&CO2_PAR
+co2_ppm = 680
+/
+"""
+
+
+def test_reference_default_namelist():
+    c = host.config_from_namelist(REFERENCE_NAMELIST)
+    assert (c.ipx, c.ipy, c.time_flux, c.time_scnr, c.year0) == (95, 38, 3, 50, 1940)
+    assert c.output_file == "output/scenario" and c.ens_id == "" and c.output_file_full == "output/scenario"
+    assert c.co2_ppm.shape == (50,) and np.all(c.co2_ppm == 680.0)
+    assert np.float32(c.physics.kappa) == np.float32(8e5) and np.float32(c.physics.co2_flux) == np.float32(298.0)
+
+
+def test_defaults_match_the_library_defaults():
+    try:
+        want = lib.default_physics()
+    except Exception as e:  # pragma: no cover - library not built
+        pytest.skip(str(e))
+    got = host._default_physics_struct()
+    for n in lib.PHYS_FIELDS + ["co2_flux"]:
+        assert np.float32(getattr(got, n)) == np.float32(getattr(want, n)), n
+    assert list(got.p_emi) == list(want.p_emi)
+
+
+def test_namelist_syntax_variants():
+    txt = """
+    &physics_par  KAPPA = 9.4E5, a_cloud=0.33 ! trailing comment
+       p_emi = (/9.0721, 106.7252, 61.5562, 0.0179, 0.0028, 0.0570, 0.3462, 2.3406, 0.7032, 1.0662/)
+       cq_latent = 2.257d6 /
+    &NUMERICS_PAR time_flux=1 time_scnr = 5
+      year0 = 2000 /
+    &diagnostics_par output_file = 'out/run', ens_id = "m07" /
+    &co2_par co2_flux = 300, co2_ppm = 400, 2*500, 600 /
+    """
+    c = host.config_from_namelist(txt)
+    assert np.float32(c.physics.kappa) == np.float32(9.4e5) and np.float32(c.physics.a_cloud) == np.float32(0.33)
+    assert np.float32(c.physics.cq_latent) == np.float32(2.257e6)
+    assert (c.time_flux, c.time_scnr, c.year0) == (1, 5, 2000)
+    assert c.output_file_full == "out/run_m07"                                   # f:1063-1068
+    assert c.co2_ppm.tolist() == [400.0, 500.0, 500.0, 600.0, 600.0]             # f:1053-1061 padding
+    assert np.float32(c.physics.co2_flux) == np.float32(300.0)
+
+
+def test_co2_padding_rules():
+    assert host.pad_co2([], 3).tolist() == [680.0, 680.0, 680.0]                 # first < 0 -> 680
+    assert host.pad_co2([350.0], 4).tolist() == [350.0] * 4
+    assert host.pad_co2([350.0, 360.0], 2).tolist() == [350.0, 360.0]
+    assert host.pad_co2([1.0, 2.0, 3.0], 0).shape == (0,)
+    try:
+        assert np.array_equal(host.pad_co2([400.0, 500.0], 5), lib.pad_co2([400.0, 500.0], 5))   # C ABI twin
+    except lib.GrebError:  # pragma: no cover - library not built
+        pass
+
+
+def test_namelist_errors():
+    with pytest.raises(host.NamelistError):
+        host.config_from_namelist("&physics_par kapa = 1 /")
+    with pytest.raises(host.NamelistError):
+        host.config_from_namelist("&numerics_par time_scnr = 2 / &co2_par co2_ppm = 1, 2, 3 /")
+    with pytest.raises(host.NamelistError):
+        host.config_from_namelist("&numerics_par time_scnr = 2")
+    with pytest.raises(host.NamelistError):
+        host.config_from_namelist("&foo a = 1 /")
+
+
+def test_output_stream_and_read_greb_roundtrip(tmp_path):
+    rng = np.random.default_rng(0)
+    monthly = rng.normal(280, 10, (2, 12, 5, 48, 96)).astype(np.float32)
+    path = tmp_path / "output" / "scenario_x"
+    host.write_output(str(path), monthly)
+    assert os.path.getsize(path) == 2 * 12 * 5 * 96 * 48 * 4                     # R/functions.R:41
+    raw = np.fromfile(path, dtype="<f4")
+    # record r (1-based) = ((year*12 + month)*5 + var); lon fastest, then lat (f:978-982)
+    assert raw[(((1 * 12 + 3) * 5 + 2) * 48 + 7) * 96 + 11] == monthly[1, 3, 2, 7, 11]
+    g = host.read_greb(str(path))
+    assert g["value"].shape == (24, 5, 48, 96) and g["variable"] == list(host.VARNAMES)
+    assert np.array_equal(g["value"].reshape(2, 12, 5, 48, 96), monthly)
+    assert g["lon"][0] == 1.875 and g["lon"][-1] == 358.125 and g["lat"][0] == -88.125 and g["lat"][-1] == 88.125
+    one = host.read_greb(str(path), varname=["albedo"], ivar=[5], nvar=5)
+    assert np.array_equal(one["value"][:, 0], monthly.reshape(24, 5, 48, 96)[:, 4])
+    with pytest.raises(ValueError):
+        host.read_greb(str(path), nvar=7)
+    # a shorter rerun does not truncate the file (the reference opens without status='replace', f:174)
+    host.write_output(str(path), monthly[:1])
+    assert os.path.getsize(path) == 2 * 12 * 5 * 96 * 48 * 4
+
+
+def test_read_inputs_reports_missing_files(tmp_path):
+    with pytest.raises(FileNotFoundError):
+        host.read_inputs(str(tmp_path))

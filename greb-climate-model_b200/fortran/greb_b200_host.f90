@@ -4,8 +4,8 @@
 !
 !  STATUS: written against the reference interfaces but NOT compiled here -- there is no Fortran
 !  compiler in the build image (gfortran / flang / nvfortran absent).  The same host logic is
-!  implemented and tested in C++ (greb-climate-model_b200/host/greb_host.cpp) and Python
-!  (greb_b200/host.py); this file is what a maintainer of sieste/greb-climate-model adds.
+!  implemented and tested in Python over the same C ABI (greb_b200/host.py: run_namelists);
+!  this file is what a maintainer of sieste/greb-climate-model adds.
 !
 !  How to use it with the reference:
 !     1. keep src/greb.f90 modules mo_numerics, mo_physics, mo_diagnostics and PROGRAM greb_run

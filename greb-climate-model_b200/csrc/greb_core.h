@@ -438,7 +438,11 @@ GDEV void helper_load_wz(HelperRow (&hr)[GREB_HROWS], const HelperGeom& g, const
 // and the polar advection (f:838-910)
 GDEV void helper_x(HelperRow& r, const HelperGeom& g, const GrebMemberConst& mc, int k) {
   const float cc2 = mc.ccx2_diff[k], cca2 = mc.ccx2_adv[k];
+#ifdef GREB_DBG_TIME2_1
+  const int time2 = 1;  // timing experiment only (wrong results)
+#else
   const int time2 = mc.time2_diff[k];
+#endif
   XRow x;
   xrow_products(x, r.T, r.W, r.WX, g.lane_l, g.lane_r);
   vf S[3], h[3];
@@ -534,18 +538,34 @@ struct SyncState {
 GDEV void circulation_main(const SimtCtx& ctx, Tile& t, const RowGeom& g, const GrebMemberConst& mc, SyncState& ss) {
   if (g.owned) tile_publish(t, g, ss.hb + (ss.phase & 1) * GNC);
   sb_arrive(ctx, ss.bar);
+#if defined(GREB_DBG_CLOCKS) && GREB_DEVICE
+  // timing experiment (tools/debug_circ.py): cycles per sub-step in the x part, the barrier and the y part
+  long long c_x = 0, c_w = 0, c_y = 0;
+#define GCLK(acc, t0) { const long long t1_ = clock64(); acc += t1_ - t0; t0 = t1_; }
+  long long tc = clock64();
+#else
+#define GCLK(acc, t0)
+#endif
   GNOUNROLL
   for (int tt = 0; tt < GSUB; ++tt) {
     vf dTx[GREB_CPT], aTx[GREB_CPT];
     substep_x(dTx, aTx, t, g, mc);                    // own row only: overlaps the barrier latency
+    GCLK(c_x, tc)
     sb_wait(ctx, ss.bar, ss.phase);
+    GCLK(c_w, tc)
     const float* buf = ss.hb + (ss.phase & 1) * GNC;
     if (g.ykind == 0) substep_y<false>(t, dTx, aTx, g, mc, buf, ss.smem);
     else substep_y<true>(t, dTx, aTx, g, mc, buf, ss.smem);
     ss.phase++;
     if (g.owned) tile_publish(t, g, ss.hb + (ss.phase & 1) * GNC);   // also after the last sub-step
     sb_arrive(ctx, ss.bar);
+    GCLK(c_y, tc)
   }
+#if defined(GREB_DBG_CLOCKS) && GREB_DEVICE
+  if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && ss.phase < 60)
+    printf("warp %2d row %2d polar %d: x %lld wait %lld y %lld cycles per sub-step\n", (int)(threadIdx.x >> 5), g.k,
+           g.polar, c_x / GSUB, c_w / GSUB, c_y / GSUB);
+#endif
   sb_wait(ctx, ss.bar, ss.phase);   // everybody's final rows are published
   if (!g.owned) tile_load_field(t, g, ss.hb + (ss.phase & 1) * GNC);
   ss.phase++;
@@ -563,12 +583,18 @@ GDEV void circulation_helper(const SimtCtx& ctx, HelperRow (&hr)[GREB_HROWS], co
       }
     }
   sb_arrive(ctx, ss.bar);
+#if defined(GREB_DBG_CLOCKS) && GREB_DEVICE
+  long long c_x = 0, c_w = 0, c_y = 0;
+  long long tc = clock64();
+#endif
   GNOUNROLL
   for (int tt = 0; tt < GSUB; ++tt) {
     GUNROLL
     for (int i = 0; i < GREB_HROWS; ++i)
       if (i < g.n) helper_x(hr[i], g, mc, g.k[i]);
+    GCLK(c_x, tc)
     sb_wait(ctx, ss.bar, ss.phase);
+    GCLK(c_w, tc)
     const float* buf = ss.hb + (ss.phase & 1) * GNC;
     ss.phase++;
     float* nxt = ss.hb + (ss.phase & 1) * GNC;
@@ -580,7 +606,13 @@ GDEV void circulation_helper(const SimtCtx& ctx, HelperRow (&hr)[GREB_HROWS], co
         for (int c = 0; c < 3; ++c) v_st(nxt, g.k[i] * GX + g.col + c, hr[i].T[c]);
       }
     sb_arrive(ctx, ss.bar);
+    GCLK(c_y, tc)
   }
+#if defined(GREB_DBG_CLOCKS) && GREB_DEVICE
+  if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && ss.phase < 60)
+    printf("helper warp %2d row %2d: x %lld wait %lld y %lld cycles per sub-step\n", (int)(threadIdx.x >> 5), g.k[0],
+           c_x / GSUB, c_w / GSUB, c_y / GSUB);
+#endif
   sb_wait(ctx, ss.bar, ss.phase);
   ss.phase++;
 }

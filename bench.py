@@ -36,6 +36,9 @@ sys.path.insert(0, os.path.join(ROOT, "greb-climate-model_b200"))
 sys.path.insert(0, ROOT)
 
 MEMBERS_PER_GPU = 1024
+# dram__bytes_read.sum + dram__bytes_write.sum of greb_member_kernel from the committed ncu --set full
+# capture (profiles/r01_v25_member_kernel_ncu_summary.txt: 6.144 GB + 0.250 GB for 148 member-years)
+NCU_DRAM_BYTES_PER_MEMBER_YEAR = (6.144290e9 + 249.916416e6) / 148
 WORKLOAD = "configs[2]: 1024-member perturbed-parameter/CO2 ensemble per GPU, 96x48, synthetic S0 forcing"
 
 
@@ -320,7 +323,9 @@ def main():
         hbm_ach = bytes_launch / (ms_launch / 1e3) / 1e9
         roofline = {
             "bound": "fp32", "achieved": achieved, "peak": peak_fp32, "unit": "TFLOP/s", "frac": achieved / peak_fp32,
-            "traffic": None,
+            "traffic": NCU_DRAM_BYTES_PER_MEMBER_YEAR * M,
+            "traffic_note": ("DRAM bytes per launch from the committed ncu capture (148-member launch, scaled to "
+                             f"{M} members); algorithmic bytes per launch = {bytes_launch:.4g}"),
             "kernel": "greb_member_kernel",
             "note": ("as-written reference flop count (greb_b200/flops.py, FMA=2) per launch / CUDA-event launch time; "
                      f"peak = 148 SMs x 128 lanes x 2 x {sm_mhz:.0f} MHz observed during the run; the reference "

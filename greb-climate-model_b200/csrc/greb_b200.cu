@@ -40,7 +40,14 @@ __global__ void __launch_bounds__(GREB_NTHREADS, 1) greb_member_kernel(const Gre
   const int member = a.member_ids[blockIdx.x];
   cta_prologue(&mc_s, a.mc + member, smem);
   SimtCtx ctx;
+#ifdef GREB_DBG_HELPER_FIRST
+  {  // experiment: helper warps on the LOWEST hardware warp ids, main warps keep their SM sub-partition
+    const int hw = threadIdx.x >> 5;
+    ctx.warp = warp_uniform(hw < 2 ? GREB_NMAIN + hw : ((hw & 3) >= 2 ? hw : hw - 4));
+  }
+#else
   ctx.warp = warp_uniform(threadIdx.x >> 5);
+#endif
   ctx.lane_u = threadIdx.x & 31;
   ctx.smem = smem;
   member_run(ctx, a, mc_s, member);
@@ -52,7 +59,14 @@ __global__ void __launch_bounds__(GREB_NTHREADS, 1) greb_circulation_kernel(cons
   __shared__ GrebMemberConst mc_s;
   cta_prologue(&mc_s, a.mc, smem);
   SimtCtx ctx;
+#ifdef GREB_DBG_HELPER_FIRST
+  {  // experiment: helper warps on the LOWEST hardware warp ids, main warps keep their SM sub-partition
+    const int hw = threadIdx.x >> 5;
+    ctx.warp = warp_uniform(hw < 2 ? GREB_NMAIN + hw : ((hw & 3) >= 2 ? hw : hw - 4));
+  }
+#else
   ctx.warp = warp_uniform(threadIdx.x >> 5);
+#endif
   ctx.lane_u = threadIdx.x & 31;
   ctx.smem = smem;
   SyncState ss;

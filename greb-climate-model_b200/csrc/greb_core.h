@@ -549,6 +549,11 @@ GDEV void circulation_main(const SimtCtx& ctx, Tile& t, const RowGeom& g, const 
   GNOUNROLL
   for (int tt = 0; tt < GSUB; ++tt) {
     vf dTx[GREB_CPT], aTx[GREB_CPT];
+#ifdef GREB_DBG_MAIN_IDLE   // timing experiment only (wrong results): main warps just synchronise
+    sb_wait(ctx, ss.bar, ss.phase);
+    const float* buf = ss.hb + (ss.phase & 1) * GNC;
+    (void)buf; (void)dTx; (void)aTx;
+#else
     substep_x(dTx, aTx, t, g, mc);                    // own row only: overlaps the barrier latency
     GCLK(c_x, tc)
     sb_wait(ctx, ss.bar, ss.phase);
@@ -556,6 +561,7 @@ GDEV void circulation_main(const SimtCtx& ctx, Tile& t, const RowGeom& g, const 
     const float* buf = ss.hb + (ss.phase & 1) * GNC;
     if (g.ykind == 0) substep_y<false>(t, dTx, aTx, g, mc, buf, ss.smem);
     else substep_y<true>(t, dTx, aTx, g, mc, buf, ss.smem);
+#endif
     ss.phase++;
     if (g.owned) tile_publish(t, g, ss.hb + (ss.phase & 1) * GNC);   // also after the last sub-step
     sb_arrive(ctx, ss.bar);

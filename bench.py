@@ -354,12 +354,31 @@ def main():
                                "sumsq_gmean": float(stats[2])},
             "nonfinite_members": int(ens.flags().sum()),
         }
+        # counters of the committed ncu --set full capture of this kernel (profiles/r01_v25_*), for context
+        line["roofline"]["ncu"] = {"ipc_per_sm": 2.49, "issue_active_pct": 62.3, "fma_pipe_active_pct": 43.1,
+                                   "lsu_wavefronts_pct": 38.4, "dram_throughput_pct": 0.84,
+                                   "registers_per_thread": 128, "source": "profiles/r01_v25_member_kernel_ncu_summary.txt"}
+        if world == 1:
+            # BASELINE.json's second metric: single-run sim-years/s (one member, one GPU, config 1 physics)
+            ens.close()
+            one = greb_b200.Ensemble(1, device=local)
+            one.set_forcing(forcing)
+            one.set_member(0, greb_b200.default_physics(), np.full(8, 680.0, dtype=np.float32))
+            one.init()
+            one.spinup(1)
+            one.reset_scenario()
+            one.run_raw(1)
+            one.run_raw(4)
+            ms1, n1 = one.last_kernel_ms()
+            line["single_run_sim_years_per_s"] = 4 / (ms1 / 1e3)
+            one.close()
         if world == 1 and not args.no_cpu_baseline:
             cb = cpu_baseline(years=6, forcing=forcing)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line), flush=True)
 
-    ens.close()
+    if getattr(ens, "h", None):
+        ens.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -912,25 +912,45 @@ GDEV void member_run_main(const SimtCtx& ctx, const GrebKernelArgs& a, const Gre
     si.co2 = co2;
     const float* forc = a.forc + (size_t)si.ityr * GF_COUNT * GNC;
 
+#if defined(GREB_DBG_CLOCKS) && GREB_DEVICE
+    // timing experiment: cycles per 12-h step in the phases of the step (block 0, thread 0)
+    long long sc0 = clock64();
+    static __shared__ long long dbg_acc[8];
+    if (it == a.it0 && threadIdx.x == 0) for (int i = 0; i < 8; ++i) dbg_acc[i] = 0;
+#define SCLK(i) { const long long t1_ = clock64(); if (threadIdx.x == 0) dbg_acc[i] += t1_ - sc0; sc0 = t1_; }
+#else
+#define SCLK(i)
+#endif
     // ---- phase A: column physics, Ts/To/cap update
     GNOUNROLL
     for (int q = 0; q < 3; ++q) column_phase_a(a, mc, member, si, g.k, g.k * GX + g.col + 4 * q, stash);
+    SCLK(0)
     tile_load_uv(t, g, forc + GF_U * GNC, forc + GF_V * GNC, smem);
     // the helper warps read the rows they circulate from global state written by the main warps
     cta_sync(ctx);
+    SCLK(1)
 
     // ---- circulation of air temperature (f:301), then of humidity (f:303): one code instance
     GNOUNROLL
     for (int fld = 0; fld < 2; ++fld) {
       tile_load_wz(t, g, wzg + fld * GNC, smem);
       tile_load_field(t, g, st + (fld == 0 ? GS_TA : GS_Q) * GNC);
+      SCLK(2)
       circulation_main(ctx, t, g, mc, ss);
+      SCLK(3)
       GUNROLL
       for (int q = 0; q < 3; ++q) {
         if (fld == 0) column_phase_b(a, member, si, g.k * GX + g.col + 4 * q, &t.T[4 * q], stash);
         else column_phase_c(a, mc, member, si, g.k * GX + g.col + 4 * q, &t.T[4 * q], stash);
       }
+      SCLK(4)
     }
+#if defined(GREB_DBG_CLOCKS) && GREB_DEVICE
+    if (it == a.it0 + a.nsteps - 1 && threadIdx.x == 0 && blockIdx.x == 0 && a.nsteps > 1)
+      printf("per step: phaseA %lld, load_uv+sync %lld, load_wz/field %lld, circulations %lld, phaseB/C %lld cycles\n",
+             dbg_acc[0] / a.nsteps, dbg_acc[1] / a.nsteps, dbg_acc[2] / a.nsteps, dbg_acc[3] / a.nsteps,
+             dbg_acc[4] / a.nsteps);
+#endif
 
     // ---- output (f:975-985)
     if (!si.spinup && si.month_end) {

@@ -53,8 +53,13 @@ GDEV vf v_mul(vf a, vf b) { return __fmul_rn(a, b); }
 GDEV vf v_div(vf a, vf b) { return __fdiv_rn(a, b); }
 GDEV vf v_abs(vf a) { return fabsf(a); }
 GDEV vf v_max(vf a, vf b) { return fmaxf(a, b); }
+#ifdef GREB_DBG_FASTMATH   // timing experiment only: approximate transcendentals
+GDEV vf v_exp(vf a) { return __expf(a); }
+GDEV vf v_log(vf a) { return __logf(a); }
+#else
 GDEV vf v_exp(vf a) { return expf(a); }
 GDEV vf v_log(vf a) { return logf(a); }
+#endif
 GDEV vb v_any_true(vb p) { return __any_sync(0xffffffffu, p); }  // uniform result
 // 4 consecutive floats, 16-byte aligned (LDG.128 / LDS.128 / STG.128 / STS.128)
 GDEV void v_ld4(vf (&o)[4], const float* p, vi idx) {

@@ -252,3 +252,64 @@ def test_default_50yr_2xco2_run_vs_oracle(oracle_mod, forcing):
     print(f"\n50-yr parity: max |dT| surf/air/ocean = {mx[0]:.2e}/{mx[1]:.2e}/{mx[2]:.2e} K, "
           f"max |dq| = {mx[3]:.2e}, max |d albedo| = {mx[4]:.2e}, cos-lat global mean {worst:.2e} K")
     ens.close()
+
+
+# ---- BASELINE.json configs[2] at full size: size-independent properties -------------------------
+
+def test_full_size_ensemble_properties(oracle_mod, forcing):
+    """1,024 perturbed-physics members (the bench workload) for one spin-up + one scenario year:
+    (a) members that were given identical parameters are bit-identical wherever they sit in the batch;
+    (b) permuting the batch permutes the results (members never interact, f:1030-1068);
+    (c) no member is flagged non-finite and every global mean is physical;
+    (d) three members, picked across the batch, match the oracle within the north_star tolerances."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from bench import member_physics
+    N = 1024
+    rng = np.random.default_rng(5)
+    src = np.arange(N)
+    dup = rng.choice(N, size=32, replace=False)
+    src[dup[16:]] = dup[:16]                       # 16 members are copies of 16 others
+    specs = [member_physics(int(s), greb_b200.default_physics) for s in src]
+    ens = greb_b200.Ensemble(N)
+    ens.set_forcing(forcing)
+    for m, (p, co2) in enumerate(specs):
+        ens.set_member(m, p, [co2])
+    ens.init()
+    ens.spinup(1)
+    ens.reset_scenario()
+    pick = [int(dup[0]), int(dup[16]), 7, 500, 1023]
+    out, gm, gc = ens.run(1, out_members=pick)
+    states = ens.get_states()
+    assert int(ens.flags().sum()) == 0
+    assert np.all(np.isfinite(gm)) and np.all(np.abs(gm) < 60.0)
+    for a, b in zip(dup[:16], dup[16:]):
+        assert np.array_equal(states[a], states[b]) and gm[a, 0] == gm[b, 0], (a, b)
+    assert np.array_equal(out[0], out[1])          # dup[0] and its copy dup[16]
+    ens.close()
+    # (b) the same members in reversed order
+    M = 64
+    sub = list(range(0, N, N // M))
+    e1 = greb_b200.Ensemble(M)
+    e2 = greb_b200.Ensemble(M)
+    for e, order in ((e1, sub), (e2, sub[::-1])):
+        e.set_forcing(forcing)
+        for m, s in enumerate(order):
+            e.set_member(m, specs[s][0], [specs[s][1]])
+        e.init()
+        e.spinup(1)
+        e.reset_scenario()
+        e.run(1, want_output=False)
+    s1, s2 = e1.get_states(), e2.get_states()
+    assert np.array_equal(s1, s2[::-1])
+    e1.close()
+    e2.close()
+    # (d) oracle check of three members
+    for i, m in ((2, 7), (3, 500), (4, 1023)):
+        p, co2 = specs[m]
+        kw = {n: getattr(p, n) for n in ("kappa", "ct_sens", "ce", "co_turb", "a_cloud", "da_ice")}
+        o = oracle_mod.Oracle(forcing, **kw)
+        o.spinup(1)
+        out_o, gm_o = o.run(1, co2)
+        check_monthly(out[i, 0], out_o[0], forcing.z_topo, o.physics, f"member {m}")
+        assert abs(float(gm[m, 0]) - float(gm_o[0])) <= TOL_GM

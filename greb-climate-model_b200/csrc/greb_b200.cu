@@ -34,6 +34,7 @@ __device__ __forceinline__ void cta_prologue(GrebMemberConst* dst, const GrebMem
 
 // One CTA integrates one ensemble member for a.nsteps 12-hour steps (time_loop, f:239-274, or
 // qflux_correction, f:325-362, selected by a.spinup).
+template <int MODE>
 __global__ void __launch_bounds__(GREB_NTHREADS, 1) greb_member_kernel(const GrebKernelArgs a) {
   extern __shared__ __align__(16) float smem[];
   __shared__ GrebMemberConst mc_s;
@@ -50,10 +51,11 @@ __global__ void __launch_bounds__(GREB_NTHREADS, 1) greb_member_kernel(const Gre
 #endif
   ctx.lane_u = threadIdx.x & 31;
   ctx.smem = smem;
-  member_run(ctx, a, mc_s, member);
+  member_run<MODE>(ctx, a, mc_s, member);
 }
 
 // circulation(X_in, dX_crcl, h_scl, wz) (f:528-553): one CTA per field
+template <int MODE>
 __global__ void __launch_bounds__(GREB_NTHREADS, 1) greb_circulation_kernel(const GrebCirculationArgs a) {
   extern __shared__ __align__(16) float smem[];
   __shared__ GrebMemberConst mc_s;
@@ -78,10 +80,10 @@ __global__ void __launch_bounds__(GREB_NTHREADS, 1) greb_circulation_kernel(cons
   if (!ctx_is_helper(ctx)) {
     const RowGeom g = row_geom(ctx, mc_s);
     Tile t;
-    tile_load_uv(t, g, a.uv, a.uv + GNC, smem);
+    tile_load_uv(t, g, a.uv, a.uv + GNC, smem, MODE == 1 ? -fast_row(g.k, mc_s).cadv : 1.0f);
     tile_load_wz(t, g, a.wz + off, smem);
     tile_load_field(t, g, a.X_in + off);
-    circulation_main(ctx, t, g, mc_s, ss);
+    circulation_main<MODE>(ctx, t, g, mc_s, ss);
 #pragma unroll
     for (int q = 0; q < 3; ++q) {
       const int idx = g.k * GX + g.col + 4 * q;
@@ -94,7 +96,7 @@ __global__ void __launch_bounds__(GREB_NTHREADS, 1) greb_circulation_kernel(cons
     HelperRow hr[GREB_HROWS];
     helper_load_uv(hr, hg, a.uv, a.uv + GNC);
     helper_load_wz(hr, hg, a.wz + off);
-    circulation_helper(ctx, hr, hg, mc_s, a.X_in + off, ss);
+    circulation_helper<MODE>(ctx, hr, hg, mc_s, a.X_in + off, ss);
   }
 }
 
@@ -124,6 +126,7 @@ struct greb_b200_handle_s {
   GrebMemberConst* d_mc = nullptr;
   cudaStream_t stream = nullptr, copy_stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_k[2] = {nullptr, nullptr}, ev_c[2] = {nullptr, nullptr};
+  int arith = GREB_ARITH_EXACT;
   int it_next = 1;   // step counter `it` of the next scenario step
   int last_out = 0;  // d_out buffer holding the last completed year
   float last_ms = 0.f;
@@ -190,8 +193,10 @@ extern "C" int greb_b200_create(greb_b200_t* out, int n_members, int device) {
     cudaEventCreateWithFlags(&h->ev_k[i], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_c[i], cudaEventDisableTiming);
   }
-  cudaFuncSetAttribute(greb_member_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GREB_SMEM_BYTES);
-  cudaFuncSetAttribute(greb_circulation_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GREB_SMEM_BYTES);
+  cudaFuncSetAttribute(greb_member_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GREB_SMEM_BYTES);
+  cudaFuncSetAttribute(greb_member_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GREB_SMEM_BYTES);
+  cudaFuncSetAttribute(greb_circulation_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GREB_SMEM_BYTES);
+  cudaFuncSetAttribute(greb_circulation_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GREB_SMEM_BYTES);
   *out = h;
   return GREB_OK;
 }
@@ -228,6 +233,19 @@ extern "C" int greb_b200_destroy(greb_b200_t h) {
   }
   delete h;
   return GREB_OK;
+}
+
+extern "C" int greb_b200_set_arithmetic(greb_b200_t h, int mode) {
+  if (!h) return GREB_E_INVALID;
+  if (mode != GREB_ARITH_EXACT && mode != GREB_ARITH_FAST)
+    return fail(h, GREB_E_INVALID, "greb_b200_set_arithmetic: mode must be GREB_ARITH_EXACT or GREB_ARITH_FAST");
+  h->arith = mode;
+  return GREB_OK;
+}
+
+static void launch_member(greb_b200_t h, int grid, const GrebKernelArgs& a) {
+  if (h->arith == GREB_ARITH_FAST) greb_member_kernel<1><<<grid, GREB_NTHREADS, GREB_SMEM_BYTES, h->stream>>>(a);
+  else greb_member_kernel<0><<<grid, GREB_NTHREADS, GREB_SMEM_BYTES, h->stream>>>(a);
 }
 
 extern "C" int greb_b200_set_forcing(greb_b200_t h, const float* z_topo, const float* glacier, const float* sw_solar,
@@ -401,7 +419,7 @@ extern "C" int greb_b200_spinup(greb_b200_t h, int years) {
   for (int y = 0; y < years; ++y) {
     a.it0 = 1 + y * GNT;
     a.nsteps = GNT;
-    greb_member_kernel<<<G, GREB_NTHREADS, GREB_SMEM_BYTES, h->stream>>>(a);
+    launch_member(h, G, a);
     h->last_launches++;
   }
   CK(cudaEventRecord(h->ev1, h->stream));
@@ -453,7 +471,7 @@ extern "C" int greb_b200_run(greb_b200_t h, int years, float* out, const int* ou
     a.nsteps = GNT;
     a.out = h->d_out[b];
     if (y >= 2 && out) CK(cudaStreamWaitEvent(h->stream, h->ev_c[b], 0));  // buffer b free again
-    greb_member_kernel<<<N, GREB_NTHREADS, GREB_SMEM_BYTES, h->stream>>>(a);
+    launch_member(h, N, a);
     h->last_launches++;
     CK(cudaGetLastError());
     h->it_next += GNT;
@@ -502,7 +520,7 @@ extern "C" int greb_b200_time_loop(greb_b200_t h, int it) {
   a.nsteps = 1;
   a.out = h->d_out[0];
   h->last_out = 0;
-  greb_member_kernel<<<h->n_members, GREB_NTHREADS, GREB_SMEM_BYTES, h->stream>>>(a);
+  launch_member(h, h->n_members, a);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(h->stream));
   h->it_next = it + 1;
@@ -603,7 +621,8 @@ extern "C" int greb_b200_circulation(greb_b200_t h, int member, int ityr, const 
   a.wz = dW;
   a.dX = dO;
   CK(cudaEventRecord(h->ev0, h->stream));
-  greb_circulation_kernel<<<n, GREB_NTHREADS, GREB_SMEM_BYTES, h->stream>>>(a);
+  if (h->arith == GREB_ARITH_FAST) greb_circulation_kernel<1><<<n, GREB_NTHREADS, GREB_SMEM_BYTES, h->stream>>>(a);
+  else greb_circulation_kernel<0><<<n, GREB_NTHREADS, GREB_SMEM_BYTES, h->stream>>>(a);
   CK(cudaEventRecord(h->ev1, h->stream));
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(h->stream));

@@ -120,14 +120,15 @@ struct Tile {
 
 GDEV float* priv_ptr(float* smem, int which, int q) { return smem + GSM_PRIV + (which * 3 + q) * (GREB_NMAIN * 32 * 4); }
 
-GDEV void tile_load_uv(Tile& t, const RowGeom& g, const float* u, const float* v, float* smem) {
+// `uscale` = 1 in the exact mode; -cadv in the fast mode (Tile::U then holds CU, see substep_x_fast)
+GDEV void tile_load_uv(Tile& t, const RowGeom& g, const float* u, const float* v, float* smem, float uscale = 1.0f) {
   GUNROLL
   for (int q = 0; q < 3; ++q) {
     vf a[4], b[4];
     v_ldg4(a, u, g.k * GX + g.col + 4 * q);
     v_ldg4(b, v, g.k * GX + g.col + 4 * q);
     GUNROLL
-    for (int i = 0; i < 4; ++i) t.U[4 * q + i] = a[i];
+    for (int i = 0; i < 4; ++i) t.U[4 * q + i] = (uscale == 1.0f) ? a[i] : a[i] * uscale;
     v_st4(priv_ptr(smem, PRIV_V, q), g.tid4, b[0], b[1], b[2], b[3]);
   }
 }
@@ -317,6 +318,110 @@ GDEV void substep_y(Tile& t, const vf (&dTx)[GREB_CPT], const vf (&aTx)[GREB_CPT
       const vf dXd = t.W[j] * (dTx[j] + dTy);   // f:721
       const vf dXa = aTx[j] + aTy;              // f:913
       t.T[j] = (T + dXd) + dXa;                 // f:549
+    }
+  }
+}
+
+// =============================================================================================
+//   FAST arithmetic mode (GREB_ARITH_FAST): the same stencils, algebraically factored and with FMA
+//   contraction — NOT bit-identical to the reference, held to the north_star tolerances instead
+//   (tests/test_gpu_fast_mode.py).  SURVEY.md A.3: the x-diffusion bracket of f:620-625 equals
+//   6(Q(j)-P(j-1)) + 3(Q(j+1)-P(j-2)) + (Q(j+2)-P(j-3)); the divisions by 20 and 3 and the factors
+//   ccx, ccy fold into one coefficient per row; (T+d)-T of the polar branches becomes d.  About 38
+//   instead of 91 instructions per cell and sub-step.  The clamps of f:715/f:907 are kept.
+// =============================================================================================
+struct FastRow {
+  float cdiff;     // ccx_diff/20 (main rows) or ccx2_diff/20 (polar rows)
+  float cadv;      // ccx_adv/3 (main rows) or ccx2_adv/20 (polar rows)
+  float cyA, cyB;  // latitudinal advection coefficient for v >= 0 / v < 0: ccy_adv/3 except on rows 2 and
+                   // ydim-1, where one branch is not divided by 3 (f:766-769, f:784-787)
+  float ccyd;
+};
+GDEV FastRow fast_row(int k, const GrebMemberConst& mc) {
+  FastRow f;
+  const int polar = mc.polar[k];
+  f.cdiff = (polar ? mc.ccx2_diff[k] : mc.ccx_diff[k]) * 0.05f;
+  f.cadv = polar ? mc.ccx2_adv[k] * 0.05f : mc.ccx_adv[k] * (1.0f / 3.0f);
+  const float c3 = mc.ccy_adv * (1.0f / 3.0f);
+  f.cyA = (k == 1) ? mc.ccy_adv : c3;
+  f.cyB = (k == GY - 2) ? mc.ccy_adv : c3;
+  f.ccyd = mc.ccy_diff;
+  return f;
+}
+
+// In the fast mode Tile::U holds CU = -u*cadv: the coefficient of the active wind branch of f:816-820 /
+// f:872-878 (u >= 0 <=> CU <= 0 selects the western branch).
+GDEV void substep_x_fast(vf (&dTx)[GREB_CPT], vf (&aTx)[GREB_CPT], const Tile& t, const RowGeom& g, const FastRow& fr) {
+  vf TT[18], WW[18];
+  GUNROLL
+  for (int i = 0; i < 3; ++i) {
+    TT[i] = v_shfl(t.T[9 + i], g.lane_l);
+    TT[15 + i] = v_shfl(t.T[i], g.lane_r);
+    WW[i] = t.wxl[i];
+    WW[15 + i] = t.wxr[i];
+  }
+  GUNROLL
+  for (int i = 0; i < GREB_CPT; ++i) {
+    TT[3 + i] = t.T[i];
+    WW[3 + i] = t.W[i];
+  }
+  vf d[17], P[17], Q[17];
+  GUNROLL
+  for (int e = 0; e < 17; ++e) d[e] = TT[e + 1] - TT[e];
+  GUNROLL
+  for (int e = 0; e <= 13; ++e) P[e] = WW[e] * d[e];
+  GUNROLL
+  for (int e = 3; e <= 16; ++e) Q[e] = WW[e + 1] * d[e];
+  // bracket = 6(Q(j)-P(j-1)) + 3(Q(j+1)-P(j-2)) + (Q(j+2)-P(j-3))
+#define GREB_FAST_S(e) \
+  v_fma(6.0f, Q[e], v_fma(-6.0f, P[(e) - 1], v_fma(3.0f, Q[(e) + 1], v_fma(-3.0f, P[(e) - 2], Q[(e) + 2] - P[(e) - 3]))))
+  if (!g.polar) {
+    GUNROLL
+    for (int j = 0; j < GREB_CPT; ++j) {
+      const int e = j + 3;
+      dTx[j] = fr.cdiff * GREB_FAST_S(e);
+      const vf SL = v_fma(WW[e - 2], TT[e] - TT[e - 2], P[e - 1]);
+      const vf SR = v_fma(WW[e + 2], TT[e + 2] - TT[e], Q[e]);
+      aTx[j] = t.U[j] * v_sel(t.U[j] <= 0.0f, SL, SR);
+    }
+  } else {
+    GUNROLL
+    for (int j = 0; j < GREB_CPT; ++j) {
+      const int e = j + 3;
+      dTx[j] = polar_clamp(fr.cdiff * GREB_FAST_S(e), t.T[j]);                         // f:715
+      const vf LL = v_fma(10.0f, P[e - 1], v_fma(4.0f, P[e - 2], P[e - 3]));
+      vf RR = v_fma(10.0f, Q[e], v_fma(4.0f, Q[e + 1], Q[e + 2]));
+      if (j == 9) RR = v_sel(g.is_bug, v_fma(10.0f, Q[e], WW[15] * (TT[15] - TT[13])), RR);   // f:881
+      aTx[j] = polar_clamp(t.U[j] * v_sel(t.U[j] <= 0.0f, LL, RR), t.T[j]);          // f:907
+    }
+  }
+#undef GREB_FAST_S
+}
+
+GDEV void substep_y_fast(Tile& t, const vf (&dTx)[GREB_CPT], const vf (&aTx)[GREB_CPT], const RowGeom& g,
+                         const FastRow& fr, const float* buf, float* smem) {
+  GUNROLL
+  for (int q = 0; q < 3; ++q) {
+    vf tm2[4], tm1[4], tp1[4], tp2[4], V[4], Wm1[4], Wp1[4], WFY[4];
+    v_ld4(V, priv_ptr(smem, PRIV_V, q), g.tid4);
+    v_ld4(Wm1, priv_ptr(smem, PRIV_WM1, q), g.tid4);
+    v_ld4(Wp1, priv_ptr(smem, PRIV_WP1, q), g.tid4);
+    v_ld4(WFY, priv_ptr(smem, PRIV_WFY, q), g.tid4);
+    v_ld4(tm1, buf, g.km1 * GX + g.col + 4 * q);
+    v_ld4(tp1, buf, g.kp1 * GX + g.col + 4 * q);
+    v_ld4(tm2, buf, g.km2 * GX + g.col + 4 * q);
+    v_ld4(tp2, buf, g.kp2 * GX + g.col + 4 * q);
+    GUNROLL
+    for (int i = 0; i < 4; ++i) {
+      const int j = 4 * q + i;
+      const vf T = t.T[j];
+      const vf PyS = Wm1[i] * (T - tm1[i]);
+      const vf QyN = Wp1[i] * (tp1[i] - T);
+      const vb pv = V[i] >= 0.0f;
+      const vf Sv = v_fma(WFY[i], T - v_sel(pv, tm2[i], tp2[i]), v_sel(pv, PyS, -QyN));
+      const vf cV = (-v_abs(V[i])) * v_sel(pv, v_bcast(fr.cyA), v_bcast(fr.cyB));
+      const vf t1 = v_fma(t.W[j], v_fma(fr.ccyd, QyN - PyS, dTx[j]), T);   // T + wz*(dTx+dTy)
+      t.T[j] = t1 + v_fma(cV, Sv, aTx[j]);                                  // + (aTx+aTy)
     }
   }
 }
@@ -522,6 +627,66 @@ GDEV void helper_y(HelperRow& r, const HelperGeom& g, const GrebMemberConst& mc,
   }
 }
 
+// ---- FAST arithmetic mode, helper rows ----------------------------------------------------------
+GDEV void xdiff_bracket3_fast(vf (&S)[3], const XRow& x) {
+  S[0] = v_fma(6.0f, x.Q0 - x.Pm1, v_fma(3.0f, x.Q1 - x.Pm2, x.Q2 - x.Pm3));
+  S[1] = v_fma(6.0f, x.Q1 - x.P0, v_fma(3.0f, x.Q2 - x.Pm1, x.Qp1 - x.Pm2));
+  S[2] = v_fma(6.0f, x.Q2 - x.P1, v_fma(3.0f, x.Qp1 - x.P0, x.Qp2 - x.Pm1));
+}
+
+GDEV void helper_x_fast(HelperRow& r, const HelperGeom& g, const GrebMemberConst& mc, int k) {
+  const FastRow fr = fast_row(k, mc);
+  const int time2 = mc.time2_diff[k];
+  XRow x;
+  xrow_products(x, r.T, r.W, r.WX, g.lane_l, g.lane_r);
+  vf S[3], h[3];
+  xdiff_bracket3_fast(S, x);
+  GUNROLL
+  for (int c = 0; c < 3; ++c) h[c] = r.T[c] + polar_clamp(fr.cdiff * S[c], r.T[c]);
+  {
+    const vf P1_[3] = {x.Pm1, x.P0, x.P1}, P2[3] = {x.Pm2, x.Pm1, x.P0}, P3[3] = {x.Pm3, x.Pm2, x.Pm1};
+    const vf Q0_[3] = {x.Q0, x.Q1, x.Q2}, Qn1[3] = {x.Q1, x.Q2, x.Qp1}, Qn2[3] = {x.Q2, x.Qp1, x.Qp2};
+    GUNROLL
+    for (int c = 0; c < 3; ++c) {
+      const vb pu = r.U[c] >= 0.0f;
+      const vf cu = (-r.U[c]) * fr.cadv;
+      const vf LL = v_fma(10.0f, P1_[c], v_fma(4.0f, P2[c], P3[c]));
+      vf RR = v_fma(10.0f, Q0_[c], v_fma(4.0f, Qn1[c], Qn2[c]));
+      if (c == 0) RR = v_sel(g.is_bug, v_fma(10.0f, Q0_[c], r.WX[2] * (x.xp1 - r.T[1])), RR);   // f:881
+      r.aTx[c] = polar_clamp(cu * v_sel(pu, LL, RR), r.T[c]);
+    }
+  }
+  GNOUNROLL
+  for (int tt2 = 1; tt2 < time2; ++tt2) {
+    XRow y;
+    xrow_products(y, h, r.W, r.WX, g.lane_l, g.lane_r);
+    xdiff_bracket3_fast(S, y);
+    GUNROLL
+    for (int c = 0; c < 3; ++c) h[c] = h[c] + polar_clamp(fr.cdiff * S[c], h[c]);
+  }
+  GUNROLL
+  for (int c = 0; c < 3; ++c) r.dTx[c] = h[c] - r.T[c];
+}
+
+GDEV void helper_y_fast(HelperRow& r, const HelperGeom& g, const GrebMemberConst& mc, int k, const float* buf) {
+  const FastRow fr = fast_row(k, mc);
+  const int km1 = k >= 1 ? k - 1 : 0, km2 = k >= 2 ? k - 2 : 0;
+  const int kp1 = k <= GY - 2 ? k + 1 : GY - 1, kp2 = k <= GY - 3 ? k + 2 : GY - 1;
+  GUNROLL
+  for (int c = 0; c < 3; ++c) {
+    const vf T = r.T[c];
+    const vf tm1 = v_ld(buf, km1 * GX + g.col + c), tp1 = v_ld(buf, kp1 * GX + g.col + c);
+    const vf tm2 = v_ld(buf, km2 * GX + g.col + c), tp2 = v_ld(buf, kp2 * GX + g.col + c);
+    const vf PyS = r.Wm1[c] * (T - tm1);      // 0 on row 1 (Wm1 = 0)
+    const vf QyN = r.Wp1[c] * (tp1 - T);      // 0 on row ydim
+    const vb pv = r.V[c] >= 0.0f;
+    const vf Sv = v_fma(r.WFY[c], T - v_sel(pv, tm2, tp2), v_sel(pv, PyS, -QyN));
+    const vf cV = (-v_abs(r.V[c])) * v_sel(pv, v_bcast(fr.cyA), v_bcast(fr.cyB));
+    const vf t1 = v_fma(r.W[c], v_fma(fr.ccyd, QyN - PyS, r.dTx[c]), T);
+    r.T[c] = t1 + v_fma(cV, Sv, r.aTx[c]);
+  }
+}
+
 // =============================================================================================
 //                                     circulation drivers
 // =============================================================================================
@@ -535,7 +700,9 @@ struct SyncState {
 // circulation (f:528-553) for a main-warp thread: on entry t.T holds X_in of the own cells, on exit
 // X after the 24 sub-steps (for rows whose circulation runs on a helper warp: read back from the
 // published field).  Every warp of the CTA (helpers via circulation_helper) must take part.
+template <int MODE = 0>
 GDEV void circulation_main(const SimtCtx& ctx, Tile& t, const RowGeom& g, const GrebMemberConst& mc, SyncState& ss) {
+  const FastRow fr = fast_row(g.k, mc);
   if (g.owned) tile_publish(t, g, ss.hb + (ss.phase & 1) * GNC);
   sb_arrive(ctx, ss.bar);
 #if defined(GREB_DBG_CLOCKS) && GREB_DEVICE
@@ -554,12 +721,14 @@ GDEV void circulation_main(const SimtCtx& ctx, Tile& t, const RowGeom& g, const 
     const float* buf = ss.hb + (ss.phase & 1) * GNC;
     (void)buf; (void)dTx; (void)aTx;
 #else
-    substep_x(dTx, aTx, t, g, mc);                    // own row only: overlaps the barrier latency
+    if (MODE == 1) substep_x_fast(dTx, aTx, t, g, fr);
+    else substep_x(dTx, aTx, t, g, mc);               // own row only: overlaps the barrier latency
     GCLK(c_x, tc)
     sb_wait(ctx, ss.bar, ss.phase);
     GCLK(c_w, tc)
     const float* buf = ss.hb + (ss.phase & 1) * GNC;
-    if (g.ykind == 0) substep_y<false>(t, dTx, aTx, g, mc, buf, ss.smem);
+    if (MODE == 1) substep_y_fast(t, dTx, aTx, g, fr, buf, ss.smem);
+    else if (g.ykind == 0) substep_y<false>(t, dTx, aTx, g, mc, buf, ss.smem);
     else substep_y<true>(t, dTx, aTx, g, mc, buf, ss.smem);
 #endif
     ss.phase++;
@@ -577,6 +746,7 @@ GDEV void circulation_main(const SimtCtx& ctx, Tile& t, const RowGeom& g, const 
   ss.phase++;
 }
 
+template <int MODE = 0>
 GDEV void circulation_helper(const SimtCtx& ctx, HelperRow (&hr)[GREB_HROWS], const HelperGeom& g,
                              const GrebMemberConst& mc, const float* X, SyncState& ss) {
   GUNROLL
@@ -597,7 +767,10 @@ GDEV void circulation_helper(const SimtCtx& ctx, HelperRow (&hr)[GREB_HROWS], co
   for (int tt = 0; tt < GSUB; ++tt) {
     GUNROLL
     for (int i = 0; i < GREB_HROWS; ++i)
-      if (i < g.n) helper_x(hr[i], g, mc, g.k[i]);
+      if (i < g.n) {
+        if (MODE == 1) helper_x_fast(hr[i], g, mc, g.k[i]);
+        else helper_x(hr[i], g, mc, g.k[i]);
+      }
     GCLK(c_x, tc)
     sb_wait(ctx, ss.bar, ss.phase);
     GCLK(c_w, tc)
@@ -607,7 +780,8 @@ GDEV void circulation_helper(const SimtCtx& ctx, HelperRow (&hr)[GREB_HROWS], co
     GUNROLL
     for (int i = 0; i < GREB_HROWS; ++i)
       if (i < g.n) {
-        helper_y(hr[i], g, mc, g.k[i], buf);
+        if (MODE == 1) helper_y_fast(hr[i], g, mc, g.k[i], buf);
+        else helper_y(hr[i], g, mc, g.k[i], buf);
         GUNROLL
         for (int c = 0; c < 3; ++c) v_st(nxt, g.k[i] * GX + g.col + c, hr[i].T[c]);
       }
@@ -643,8 +817,14 @@ struct StepInfo {
 
 // Phase A (before the circulations): SW, LW, sensible, hydro, deep ocean; Ts/To/cap_surf update,
 // flux corrections in spin-up mode; stashes the air-temperature and humidity tendencies.
+// MODE 1 (GREB_ARITH_FAST): approximate division and transcendentals (2 ulp); MODE 0: IEEE division and
+// the CUDA libm, like the reference's true divisions
+template <int MODE>
 GDEV void column_phase_a(const GrebKernelArgs& a, const GrebMemberConst& mc, int member, const StepInfo& si, int k,
                          vi idx0, float* stash) {
+#define DIVF(x, y) (MODE == 1 ? v_div_fast((x), (y)) : (x) / (y))
+#define LOGF(x) (MODE == 1 ? v_log_fast(x) : v_log(x))
+#define EXPF(x) (MODE == 1 ? v_exp_fast(x) : v_exp(x))
   const float* forc = a.forc + (size_t)si.ityr * GF_COUNT * GNC;
   float* st = a.state + (size_t)member * GS_COUNT * GNC;
   float* acc = a.acc + (size_t)member * GA_COUNT * GNC;
@@ -695,7 +875,7 @@ GDEV void column_phase_a(const GrebKernelArgs& a, const GrebMemberConst& mc, int
     const float a_ice = mc.a_no_ice + mc.da_ice;
     const vf T1 = v_sel(land_ge0, v_bcast(mc.Tl_ice1), v_bcast(mc.To_ice1));
     const vf T2 = v_sel(land_ge0, v_bcast(mc.Tl_ice2), v_bcast(mc.To_ice2));
-    vf a_surf = mc.a_no_ice + mc.da_ice * (1.0f - (Ts - T1) / (T2 - T1));
+    vf a_surf = mc.a_no_ice + mc.da_ice * (1.0f - DIVF(Ts - T1, T2 - T1));
     a_surf = v_sel(Ts <= T1, v_bcast(a_ice), a_surf);
     a_surf = v_sel(Ts >= T2, v_bcast(mc.a_no_ice), a_surf);
     a_surf = v_sel(glac, v_bcast(a_ice), a_surf);
@@ -705,9 +885,9 @@ GDEV void column_phase_a(const GrebKernelArgs& a, const GrebMemberConst& mc, int
     // ---- LWradiation, f:420-432
     const vf e_co2 = ez * si.co2;
     const vf e_vapor = ez * mc.r_qviwv * q;
-    vf em = pe[3] * v_log(pe[0] * e_co2 + pe[1] * e_vapor + pe[2]) + pe[6] + pe[4] * v_log(pe[0] * e_co2 + pe[2]) +
-            pe[5] * v_log(pe[1] * e_vapor + pe[2]);
-    em = (pe[7] - cld) / pe[8] * (em - pe[9]) + pe[9];
+    vf em = pe[3] * LOGF(pe[0] * e_co2 + pe[1] * e_vapor + pe[2]) + pe[6] + pe[4] * LOGF(pe[0] * e_co2 + pe[2]) +
+            pe[5] * LOGF(pe[1] * e_vapor + pe[2]);
+    em = DIVF(pe[7] - cld, v_bcast(pe[8])) * (em - pe[9]) + pe[9];
     const vf LWsurf = -(mc.sig * pow4(Ts));
     const vf LWdown = -(em * mc.sig * pow4(Ta + dTrad));
     const vf LWup = LWdown;
@@ -716,39 +896,39 @@ GDEV void column_phase_a(const GrebKernelArgs& a, const GrebMemberConst& mc, int
     const vf Qsens = mc.ct_sens * (Ta - Ts);
 
     // ---- hydro, f:457-467 (abswind incl. gustiness is precomputed on the host, f:452-454)
-    vf qs = 3.75e-3f * v_exp(17.08085f * (Ts - 273.15f) / (Ts - 273.15f + 234.175f));
+    vf qs = 3.75e-3f * EXPF(DIVF(17.08085f * (Ts - 273.15f), Ts - 273.15f + 234.175f));
     qs = qs * ez;
     const vf Qlat = (q - qs) * absw * mc.cq_latent * mc.rho_air * mc.ce * swet;
-    const vf dq_eva = -(Qlat / mc.cq_latent / mc.r_qviwv);
+    const vf dq_eva = -(DIVF(DIVF(Qlat, v_bcast(mc.cq_latent)), v_bcast(mc.r_qviwv)));
     const vf dq_rain = mc.cq_rain * q;
     const vf Qlat_air = -(dq_rain * mc.cq_latent * mc.r_qviwv);
 
     // ---- deep_ocean, f:505-523
     const vb warm = ocean && (Ts >= mc.To_ice2);
-    vf dTo = v_sel(warm && (dmld < 0.0f), -(dmld / (zoc - mld) * (Ts - To)), v_bcast(0.0f));
-    vf dToc = v_sel(warm && (dmld > 0.0f), dmld / mld * (To - Ts), v_bcast(0.0f));
+    vf dTo = v_sel(warm && (dmld < 0.0f), -(DIVF(dmld, zoc - mld) * (Ts - To)), v_bcast(0.0f));
+    vf dToc = v_sel(warm && (dmld > 0.0f), DIVF(dmld, mld) * (To - Ts), v_bcast(0.0f));
     dTo = 0.5f * dTo;
     dToc = 0.5f * dToc;
     const vf Tx = v_max(v_bcast(mc.To_ice2), Ts);
-    dTo = dTo + GREB_DT * mc.co_turb * (Tx - To) / (mc.cap_ocean * (zoc - mld));
-    dToc = dToc + GREB_DT * mc.co_turb * (To - Tx) / (mc.cap_ocean * mld);
+    dTo = dTo + DIVF(GREB_DT * mc.co_turb * (Tx - To), mc.cap_ocean * (zoc - mld));
+    dToc = dToc + DIVF(GREB_DT * mc.co_turb * (To - Tx), mc.cap_ocean * mld);
 
     vf Ts0, To0;
-    tendA4[i] = GREB_DT * (LWup + LWdown - em * LWsurf + Qlat_air - Qsens) / mc.cap_air;  // f:260 / f:336
+    tendA4[i] = DIVF(GREB_DT * (LWup + LWdown - em * LWsurf + Qlat_air - Qsens), v_bcast(mc.cap_air));  // f:260 / f:336
     tq4[i] = GREB_DT * (dq_eva + dq_rain);                                                // f:264 / f:341
     if (!si.spinup) {  // time_loop, f:258-262
-      Ts0 = Ts + dToc + GREB_DT * (sw + LWsurf - LWdown + Qlat + Qsens + c1[i]) / cap;
+      Ts0 = Ts + dToc + DIVF(GREB_DT * (sw + LWsurf - LWdown + Qlat + Qsens + c1[i]), cap);
       To0 = To + dTo + c2[i];
       tfo[i] = c1[i];
       tofo[i] = c2[i];
     } else {  // qflux_correction, f:333-351
-      const vf dTs = GREB_DT * (sw + LWsurf - LWdown + Qlat + Qsens) / cap;
+      const vf dTs = DIVF(GREB_DT * (sw + LWsurf - LWdown + Qlat + Qsens), cap);
       const vf ts0 = Ts + dTs + dToc;
       const vf to0 = To + dTo;
       const vf T_error = c1[i] - ts0;
-      const vf tf = T_error * cap / GREB_DT;
+      const vf tf = DIVF(T_error * cap, v_bcast(GREB_DT));
       tfo[i] = tf;
-      Ts0 = Ts + dTs + dToc + tf * GREB_DT / cap;
+      Ts0 = Ts + dTs + dToc + DIVF(tf * GREB_DT, cap);
       const vf tof = c2[i] - to0;
       tofo[i] = tof;
       To0 = To + dTo + tof;
@@ -758,7 +938,7 @@ GDEV void column_phase_a(const GrebKernelArgs& a, const GrebMemberConst& mc, int
     vf capn = cap;
     {
       const vf capo = mc.cap_ocean * mld;
-      vf ramp = mc.cap_land + (capo - mc.cap_land) / (mc.To_ice2 - mc.To_ice1) * (Ts0 - mc.To_ice1);
+      vf ramp = mc.cap_land + DIVF(capo - mc.cap_land, v_bcast(mc.To_ice2 - mc.To_ice1)) * (Ts0 - mc.To_ice1);
       ramp = v_sel(Ts0 <= mc.To_ice1, v_bcast(mc.cap_land), ramp);
       ramp = v_sel(Ts0 >= mc.To_ice2, capo, ramp);
       capn = v_sel(ocean, ramp, capn);
@@ -784,6 +964,9 @@ GDEV void column_phase_a(const GrebKernelArgs& a, const GrebMemberConst& mc, int
     v_st4(corr + GC_TF * GNC, idx0, tfo[0], tfo[1], tfo[2], tfo[3]);
     v_st4(corr + GC_TOF * GNC, idx0, tofo[0], tofo[1], tofo[2], tofo[3]);
   }
+#undef DIVF
+#undef LOGF
+#undef EXPF
 }
 
 // Phase B: after circulation(Ta).  X = circulated air temperature of 4 cells.
@@ -895,6 +1078,7 @@ GDEV StepInfo step_info(const GrebKernelArgs& a, const GrebMemberConst& mc, int 
 // `smem` layout: greb_types.h GSM_*.  The SplitBar and the flags must have been initialised
 // (sb_init with the number of arriving units, flags = 0) before the first call.
 // =============================================================================================
+template <int MODE = 0>
 GDEV void member_run_main(const SimtCtx& ctx, const GrebKernelArgs& a, const GrebMemberConst& mc, int member,
                           SyncState& ss) {
   float* smem = ctx.smem;
@@ -923,9 +1107,9 @@ GDEV void member_run_main(const SimtCtx& ctx, const GrebKernelArgs& a, const Gre
 #endif
     // ---- phase A: column physics, Ts/To/cap update
     GNOUNROLL
-    for (int q = 0; q < 3; ++q) column_phase_a(a, mc, member, si, g.k, g.k * GX + g.col + 4 * q, stash);
+    for (int q = 0; q < 3; ++q) column_phase_a<MODE>(a, mc, member, si, g.k, g.k * GX + g.col + 4 * q, stash);
     SCLK(0)
-    tile_load_uv(t, g, forc + GF_U * GNC, forc + GF_V * GNC, smem);
+    tile_load_uv(t, g, forc + GF_U * GNC, forc + GF_V * GNC, smem, MODE == 1 ? -fast_row(g.k, mc).cadv : 1.0f);
     // the helper warps read the rows they circulate from global state written by the main warps
     cta_sync(ctx);
     SCLK(1)
@@ -936,7 +1120,7 @@ GDEV void member_run_main(const SimtCtx& ctx, const GrebKernelArgs& a, const Gre
       tile_load_wz(t, g, wzg + fld * GNC, smem);
       tile_load_field(t, g, st + (fld == 0 ? GS_TA : GS_Q) * GNC);
       SCLK(2)
-      circulation_main(ctx, t, g, mc, ss);
+      circulation_main<MODE>(ctx, t, g, mc, ss);
       SCLK(3)
       GUNROLL
       for (int q = 0; q < 3; ++q) {
@@ -993,6 +1177,7 @@ GDEV void member_run_main(const SimtCtx& ctx, const GrebKernelArgs& a, const Gre
 }
 
 // the helper warps' view of the same step sequence (identical barrier pattern)
+template <int MODE = 0>
 GDEV void member_run_helper(const SimtCtx& ctx, const GrebKernelArgs& a, const GrebMemberConst& mc, int member,
                             SyncState& ss) {
   const float* st = a.state + (size_t)member * GS_COUNT * GNC;
@@ -1008,7 +1193,7 @@ GDEV void member_run_helper(const SimtCtx& ctx, const GrebKernelArgs& a, const G
     GNOUNROLL
     for (int fld = 0; fld < 2; ++fld) {
       helper_load_wz(hr, hg, wzg + fld * GNC);
-      circulation_helper(ctx, hr, hg, mc, st + (fld == 0 ? GS_TA : GS_Q) * GNC, ss);
+      circulation_helper<MODE>(ctx, hr, hg, mc, st + (fld == 0 ? GS_TA : GS_Q) * GNC, ss);
     }
     if (ityr == GNT - 1) {
       cta_sync(ctx);
@@ -1018,12 +1203,13 @@ GDEV void member_run_helper(const SimtCtx& ctx, const GrebKernelArgs& a, const G
   }
 }
 
+template <int MODE = 0>
 GDEV void member_run(const SimtCtx& ctx, const GrebKernelArgs& a, const GrebMemberConst& mc, int member) {
   SyncState ss;
   ss.bar = reinterpret_cast<SplitBar*>(ctx.smem + GSM_SYNC);
   ss.hb = ctx.smem + GSM_HB;
   ss.smem = ctx.smem;
   ss.phase = 0;
-  if (ctx_is_helper(ctx)) member_run_helper(ctx, a, mc, member, ss);
-  else member_run_main(ctx, a, mc, member, ss);
+  if (ctx_is_helper(ctx)) member_run_helper<MODE>(ctx, a, mc, member, ss);
+  else member_run_main<MODE>(ctx, a, mc, member, ss);
 }

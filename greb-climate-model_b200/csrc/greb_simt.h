@@ -60,6 +60,10 @@ GDEV vf v_log(vf a) { return __logf(a); }
 GDEV vf v_exp(vf a) { return expf(a); }
 GDEV vf v_log(vf a) { return logf(a); }
 #endif
+// approximate forms of the fast arithmetic mode (max error 2 ulp; never used in the exact mode)
+GDEV vf v_div_fast(vf a, vf b) { return __fdividef(a, b); }
+GDEV vf v_log_fast(vf a) { return __logf(a); }
+GDEV vf v_exp_fast(vf a) { return __expf(a); }
 GDEV vb v_any_true(vb p) { return __any_sync(0xffffffffu, p); }  // uniform result
 // 4 consecutive floats, 16-byte aligned (LDG.128 / LDS.128 / STG.128 / STS.128)
 GDEV void v_ld4(vf (&o)[4], const float* p, vi idx) {
@@ -189,6 +193,9 @@ GDEV vf v_abs(vf a) { vf r; for (int l = 0; l < GW; ++l) r.v[l] = fabsf(a.v[l]);
 GDEV vf v_exp(vf a) { vf r; for (int l = 0; l < GW; ++l) r.v[l] = expf(a.v[l]); return r; }
 GDEV vf v_log(vf a) { vf r; for (int l = 0; l < GW; ++l) r.v[l] = logf(a.v[l]); return r; }
 GDEV vf v_bcast(float x) { return vf(x); }
+GDEV vf v_div_fast(vf a, vf b) { return v_div(a, b); }   // the emulator has no approximate forms
+GDEV vf v_log_fast(vf a) { return v_log(a); }
+GDEV vf v_exp_fast(vf a) { return v_exp(a); }
 GDEV vf v_shfl(vf x, vi src) { vf r; for (int l = 0; l < GW; ++l) r.v[l] = x.v[src.v[l] & 31]; return r; }
 GDEV vf v_sel(vb p, vf a, vf b) { vf r; for (int l = 0; l < GW; ++l) r.v[l] = p.v[l] ? a.v[l] : b.v[l]; return r; }
 GDEV vi v_seli(vb p, vi a, vi b) { vi r; for (int l = 0; l < GW; ++l) r.v[l] = p.v[l] ? a.v[l] : b.v[l]; return r; }

@@ -22,7 +22,7 @@ PHYS_FIELDS = ["pi", "sig", "rho_ocean", "rho_land", "rho_air", "cp_ocean", "cp_
 
 # every symbol include/greb_b200.h declares
 ABI_SYMBOLS = ["greb_b200_physics_defaults", "greb_b200_physics_original", "greb_b200_create", "greb_b200_destroy",
-               "greb_b200_last_error", "greb_b200_n_members", "greb_b200_set_forcing", "greb_b200_set_member",
+               "greb_b200_last_error", "greb_b200_n_members", "greb_b200_set_arithmetic", "greb_b200_set_forcing", "greb_b200_set_member",
                "greb_b200_pad_co2", "greb_b200_init", "greb_b200_spinup", "greb_b200_reset_scenario",
                "greb_b200_run", "greb_b200_time_loop", "greb_b200_get_state", "greb_b200_set_state",
                "greb_b200_get_states", "greb_b200_set_states",
@@ -83,6 +83,7 @@ def load_library():
     L.greb_b200_last_error.argtypes = [vp]
     L.greb_b200_last_error.restype = C.c_char_p
     L.greb_b200_n_members.argtypes = [vp]
+    L.greb_b200_set_arithmetic.argtypes = [vp, C.c_int]
     L.greb_b200_set_forcing.argtypes = [vp] + [fp] * 10
     L.greb_b200_set_member.argtypes = [vp, C.c_int, C.POINTER(Physics), fp, C.c_int, C.c_int]
     L.greb_b200_pad_co2.argtypes = [fp, C.c_int, fp, C.c_int]
@@ -168,6 +169,11 @@ class Ensemble:
     def _ck(self, rc, what):
         if rc != 0:
             raise GrebError(f"{what} failed ({rc}): {self.L.greb_b200_last_error(self.h).decode()}")
+
+    def set_arithmetic(self, mode: str):
+        """'exact' (default: bit-identical circulation) or 'fast' (factored stencils + FMA, within the
+        north_star tolerances); include/greb_b200.h GREB_ARITH_*."""
+        self._ck(self.L.greb_b200_set_arithmetic(self.h, {"exact": 0, "fast": 1}[mode]), "greb_b200_set_arithmetic")
 
     def set_forcing(self, f):
         arrs = [_f(a) for a in (f.z_topo, f.glacier, f.sw_solar, f.tclim, f.qclim, f.swetclim, f.uclim, f.vclim,

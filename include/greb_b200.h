@@ -76,6 +76,16 @@ int greb_b200_n_members(greb_b200_t h);
 
 /* The ten input fields PROGRAM greb_run reads (src/greb.f90:1073-1085) — shared by all members.
  * Toclim is derived inside exactly as src/greb.f90:1087-1094.  Copies to the device once. */
+/* Arithmetic of the circulation kernels.  GREB_ARITH_EXACT (default): IEEE fp32 in the reference's
+ * expression order, no FMA contraction — diffusion/advection/circulation are bit-identical to the
+ * reference built with its own flags (Makefile:5-13).  GREB_ARITH_FAST: the same stencils
+ * algebraically factored with FMA contraction, 2.4x fewer instructions; results
+ * agree with the reference within the tolerances of BASELINE.json (per-cell monthly T <= 0.01 K,
+ * q <= 1e-6, global mean <= 1e-3 K over the 50-year run) instead of bit for bit.  May be changed
+ * between launches. */
+enum { GREB_ARITH_EXACT = 0, GREB_ARITH_FAST = 1 };
+int greb_b200_set_arithmetic(greb_b200_t h, int mode);
+
 int greb_b200_set_forcing(greb_b200_t h, const float* z_topo /*[48][96]*/, const float* glacier /*[48][96]*/,
                           const float* sw_solar /*[730][48]*/, const float* tclim /*[730][48][96]*/,
                           const float* qclim, const float* swetclim, const float* uclim, const float* vclim,

@@ -11,6 +11,8 @@ om.build()
 f = synth.cached_forcing(cache_dir="/tmp/greb_b200_cache")
 o = om.Oracle(f)
 ens = greb_b200.Ensemble(1)
+if "--fast" in sys.argv:
+    ens.set_arithmetic("fast")
 ens.set_forcing(f)
 ens.set_member(0, greb_b200.default_physics(), [680.0])
 ens.init()

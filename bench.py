@@ -37,8 +37,18 @@ sys.path.insert(0, ROOT)
 
 MEMBERS_PER_GPU = 1024
 # dram__bytes_read.sum + dram__bytes_write.sum of greb_member_kernel from the committed ncu --set full
-# capture (profiles/r01_v25_member_kernel_ncu_summary.txt: 6.144 GB + 0.250 GB for 148 member-years)
-NCU_DRAM_BYTES_PER_MEMBER_YEAR = (6.144290e9 + 249.916416e6) / 148
+# captures (148 member-years per launch): fast mode profiles/r01_final_fast_member_kernel_ncu_summary.txt,
+# exact mode profiles/r01_v25_member_kernel_ncu_summary.txt
+NCU = {
+    "fast": {"dram_bytes_per_member_year": (6.386314e9 + 213.976320e6) / 148, "ipc_per_sm": 2.26,
+             "issue_active_pct": 56.6, "fma_pipe_inst_pct": 36.5, "alu_pipe_inst_pct": 25.4,
+             "lsu_wavefronts_pct": 52.5, "warp_instructions_per_member_year": 40717764268 / 148,
+             "registers_per_thread": 128, "source": "profiles/r01_final_fast_member_kernel_ncu_summary.txt"},
+    "exact": {"dram_bytes_per_member_year": (6.144290e9 + 249.916416e6) / 148, "ipc_per_sm": 2.49,
+              "issue_active_pct": 62.3, "fma_pipe_inst_pct": 43.0, "alu_pipe_inst_pct": 25.6,
+              "lsu_wavefronts_pct": 38.4, "warp_instructions_per_member_year": 66605095626 / 148,
+              "registers_per_thread": 128, "source": "profiles/r01_v25_member_kernel_ncu_summary.txt"},
+}
 WORKLOAD = "configs[2]: 1024-member perturbed-parameter/CO2 ensemble per GPU, 96x48, synthetic S0 forcing"
 
 
@@ -188,6 +198,9 @@ def main():
     ap.add_argument("--members", type=int, default=MEMBERS_PER_GPU, help="members per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--arith", default="fast", choices=["fast", "exact"],
+                    help="fast (default): factored stencils + FMA, results within the BASELINE.json tolerances; "
+                         "exact: bit-identical circulation (IEEE order of the reference, no FMA)")
     ap.add_argument("--shared-physics", action="store_true",
                     help="CO2-only ensemble (config 3 (i)): one shared spin-up and correction set")
     args = ap.parse_args()
@@ -214,10 +227,11 @@ def main():
 
     M = args.members
     K, W = args.steps, max(args.warmup, 0)
-    n_years = W + K + 4
+    n_years = W + K + 8
     forcing = synth.cached_forcing(cache_dir=os.environ.get("GREB_FORCING_CACHE", "/tmp/greb_b200_cache"))
 
     ens = greb_b200.Ensemble(M, device=local)
+    ens.set_arithmetic(args.arith)
     ens.set_forcing(forcing)
     flops_year = 0.0
     first, last = sharding.shard_range(M * world, world, rank)   # weak scaling: M members per rank
@@ -323,7 +337,7 @@ def main():
         hbm_ach = bytes_launch / (ms_launch / 1e3) / 1e9
         roofline = {
             "bound": "fp32", "achieved": achieved, "peak": peak_fp32, "unit": "TFLOP/s", "frac": achieved / peak_fp32,
-            "traffic": NCU_DRAM_BYTES_PER_MEMBER_YEAR * M,
+            "traffic": NCU[args.arith]["dram_bytes_per_member_year"] * M,
             "traffic_note": ("DRAM bytes per launch from the committed ncu capture (148-member launch, scaled to "
                              f"{M} members); algorithmic bytes per launch = {bytes_launch:.4g}"),
             "kernel": "greb_member_kernel",
@@ -343,7 +357,11 @@ def main():
                        "step": "one simulated year (730 steps, 12 month-end outputs x 5 fields) for every member",
                        "physics": "shared (CO2-only)" if args.shared_physics else "perturbed per member",
                        "l2": "inputs larger than L2 (per-member flux corrections 40 MB x members)",
-                       "arithmetic": "exact mode (no FMA contraction, IEEE divisions)"},
+                       "arithmetic": ("fast mode (GREB_ARITH_FAST: factored stencils, FMA contraction, approximate "
+                                      "division/log/exp in the column physics; 50-year run within 7e-4 K / 6e-8 kg/kg "
+                                      "of the reference, gates 1e-2 K / 1e-6: tests/test_gpu_fast_mode.py)"
+                                      if args.arith == "fast" else
+                                      "exact mode (no FMA contraction, IEEE divisions; circulation bit-identical)")},
             "roofline": roofline,
             "e2e": e2e,
             "gpu_launches": launches,
@@ -355,13 +373,25 @@ def main():
             "nonfinite_members": int(ens.flags().sum()),
         }
         # counters of the committed ncu --set full capture of this kernel (profiles/r01_v25_*), for context
-        line["roofline"]["ncu"] = {"ipc_per_sm": 2.49, "issue_active_pct": 62.3, "fma_pipe_active_pct": 43.1,
-                                   "lsu_wavefronts_pct": 38.4, "dram_throughput_pct": 0.84,
-                                   "registers_per_thread": 128, "source": "profiles/r01_v25_member_kernel_ncu_summary.txt"}
+        line["roofline"]["ncu"] = NCU[args.arith]
+        line["roofline"]["executed_fp32_note"] = (
+            "frac uses the reference's AS-WRITTEN flop count; the fast mode executes 2.4x fewer instructions "
+            "(factored stencils), see roofline.ncu.warp_instructions_per_member_year and issue_active_pct for "
+            "the real machine utilisation")
+        if world == 1 and args.arith == "fast":
+            # the same workload in the exact arithmetic mode (bit-identical circulation), 2 timed years
+            ens.set_arithmetic("exact")
+            ens.run_raw(1)
+            ens.run_raw(2)
+            ms_e, n_e = ens.last_kernel_ms()
+            line["exact_mode"] = {"value": M * 2 / (ms_e / 1e3), "unit": "member-years/s",
+                                  "note": "GREB_ARITH_EXACT: IEEE order of the reference, no FMA contraction"}
+            ens.set_arithmetic("fast")
         if world == 1:
             # BASELINE.json's second metric: single-run sim-years/s (one member, one GPU, config 1 physics)
             ens.close()
             one = greb_b200.Ensemble(1, device=local)
+            one.set_arithmetic(args.arith)
             one.set_forcing(forcing)
             one.set_member(0, greb_b200.default_physics(), np.full(8, 680.0, dtype=np.float32))
             one.init()

@@ -80,7 +80,11 @@ __global__ void __launch_bounds__(GREB_NTHREADS, 1) greb_circulation_kernel(cons
   if (!ctx_is_helper(ctx)) {
     const RowGeom g = row_geom(ctx, mc_s);
     Tile t;
-    tile_load_uv(t, g, a.uv, a.uv + GNC, smem, MODE == 1 ? -fast_row(g.k, mc_s).cadv : 1.0f);
+    {
+      const FastRow fr = fast_row(g.k, mc_s);
+      tile_load_uv(t, g, a.uv, a.uv + GNC, smem, MODE == 1 ? -fr.cadv : 1.0f, MODE == 1 ? fr.cyA : 1.0f,
+                   MODE == 1 ? fr.cyB : 1.0f);
+    }
     tile_load_wz(t, g, a.wz + off, smem);
     tile_load_field(t, g, a.X_in + off);
     circulation_main<MODE>(ctx, t, g, mc_s, ss);

@@ -120,15 +120,21 @@ struct Tile {
 
 GDEV float* priv_ptr(float* smem, int which, int q) { return smem + GSM_PRIV + (which * 3 + q) * (GREB_NMAIN * 32 * 4); }
 
-// `uscale` = 1 in the exact mode; -cadv in the fast mode (Tile::U then holds CU, see substep_x_fast)
-GDEV void tile_load_uv(Tile& t, const RowGeom& g, const float* u, const float* v, float* smem, float uscale = 1.0f) {
+// `uscale` = 1 in the exact mode; -cadv in the fast mode (Tile::U then holds CU, see substep_x_fast).
+// `vA`, `vB` = 1 in the exact mode; in the fast mode the latitudinal advection coefficient for v >= 0 /
+// v < 0, so that the private V slot holds v*cy: its sign selects the wind branch, -|v*cy| is the factor.
+GDEV void tile_load_uv(Tile& t, const RowGeom& g, const float* u, const float* v, float* smem, float uscale = 1.0f,
+                       float vA = 1.0f, float vB = 1.0f) {
   GUNROLL
   for (int q = 0; q < 3; ++q) {
     vf a[4], b[4];
     v_ldg4(a, u, g.k * GX + g.col + 4 * q);
     v_ldg4(b, v, g.k * GX + g.col + 4 * q);
     GUNROLL
-    for (int i = 0; i < 4; ++i) t.U[4 * q + i] = (uscale == 1.0f) ? a[i] : a[i] * uscale;
+    for (int i = 0; i < 4; ++i) {
+      t.U[4 * q + i] = (uscale == 1.0f) ? a[i] : a[i] * uscale;
+      if (vA != 1.0f || vB != 1.0f) b[i] = b[i] * v_sel(b[i] >= 0.0f, v_bcast(vA), v_bcast(vB));
+    }
     v_st4(priv_ptr(smem, PRIV_V, q), g.tid4, b[0], b[1], b[2], b[3]);
   }
 }
@@ -419,9 +425,8 @@ GDEV void substep_y_fast(Tile& t, const vf (&dTx)[GREB_CPT], const vf (&aTx)[GRE
       const vf QyN = Wp1[i] * (tp1[i] - T);
       const vb pv = V[i] >= 0.0f;
       const vf Sv = v_fma(WFY[i], T - v_sel(pv, tm2[i], tp2[i]), v_sel(pv, PyS, -QyN));
-      const vf cV = (-v_abs(V[i])) * v_sel(pv, v_bcast(fr.cyA), v_bcast(fr.cyB));
       const vf t1 = v_fma(t.W[j], v_fma(fr.ccyd, QyN - PyS, dTx[j]), T);   // T + wz*(dTx+dTy)
-      t.T[j] = t1 + v_fma(cV, Sv, aTx[j]);                                  // + (aTx+aTy)
+      t.T[j] = t1 + v_fma(-v_abs(V[i]), Sv, aTx[j]);                        // + (aTx+aTy); V holds v*cy
     }
   }
 }
@@ -1109,7 +1114,11 @@ GDEV void member_run_main(const SimtCtx& ctx, const GrebKernelArgs& a, const Gre
     GNOUNROLL
     for (int q = 0; q < 3; ++q) column_phase_a<MODE>(a, mc, member, si, g.k, g.k * GX + g.col + 4 * q, stash);
     SCLK(0)
-    tile_load_uv(t, g, forc + GF_U * GNC, forc + GF_V * GNC, smem, MODE == 1 ? -fast_row(g.k, mc).cadv : 1.0f);
+    {
+      const FastRow fr = fast_row(g.k, mc);
+      tile_load_uv(t, g, forc + GF_U * GNC, forc + GF_V * GNC, smem, MODE == 1 ? -fr.cadv : 1.0f,
+                   MODE == 1 ? fr.cyA : 1.0f, MODE == 1 ? fr.cyB : 1.0f);
+    }
     // the helper warps read the rows they circulate from global state written by the main warps
     cta_sync(ctx);
     SCLK(1)

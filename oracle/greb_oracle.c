@@ -1,9 +1,13 @@
 /*
  * greb_oracle.c — CPU restatement of the reference GREB time-stepping core (see greb_oracle.h).
  *
- * TEST INFRASTRUCTURE ONLY (parity oracle + CPU baseline).  PARITY UNPINNED by the reference
- * (no golden vectors exist upstream, no Fortran compiler here) — see the header for how it is
- * pinned instead.
+ * TEST INFRASTRUCTURE ONLY (parity oracle + CPU baseline).  The reference ships no golden vectors
+ * and the image has no Fortran compiler; this restatement is PINNED bit for bit against the
+ * reference's own source, machine-translated statement by statement and compiled here
+ * (oracle/f90_to_cpp.py -> oracle/_ref/, driven by oracle/ref.py), and against the golden vectors
+ * generated from it (tests/golden/, tests/test_golden.py, tests/test_ref_pin.py): every kernel
+ * routine, the default 3+50-year run (all 3,000 records), a perturbed member, the greb-original
+ * control + scenario run.
  *
  * Conventions: Fortran X(i,k) (i = longitude 1..96 fastest, k = latitude 1..48) is C x[k-1][i-1].
  * All comments "f:NNN" cite /root/reference/src/greb.f90 line numbers.

@@ -5,14 +5,17 @@
  * product path (greb-climate-model_b200/, include/) may include, link or call it.  Only
  * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs use it.
  *
- * PARITY UNPINNED BY THE REFERENCE: sieste/greb-climate-model ships no tests, golden
- * vectors or stored outputs, there is no Fortran compiler in this image, and 7 of the 10
- * input files are absent, so the reference itself cannot be run.  The restatement is pinned by
- *   (a) a second, independent NumPy-float32 transcription (tests/np_greb.py),
- *   (b) a mechanical F90->NumPy transliteration of the reference's own source text for the
- *       stencil routines (tools/f90_stencil_check.py, run where /root/reference exists;
- *       its vectors are committed under tests/golden/),
- *   (c) the property / known-answer / bug-compatibility tests listed in SURVEY.md section 4.
+ * HOW IT IS PINNED: sieste/greb-climate-model ships no tests, golden vectors or stored outputs,
+ * there is no Fortran compiler in this image, and 7 of the 10 input files are absent (synthetic
+ * inputs in the reference's binary format are used, greb_b200/synth.py).  The reference is
+ * nevertheless executed here: oracle/f90_to_cpp.py translates its Fortran modules and
+ * subroutines mechanically into C++ from the source tree where it lies, oracle/ref.py drives the
+ * compiled result (oracle/_ref/) like PROGRAM greb_run does, and this restatement is compared
+ * with it BIT FOR BIT — every kernel routine, the default 3+50-year run (3,000 records), a
+ * perturbed member, the greb-original control + scenario run (tests/test_ref_pin.py; golden
+ * vectors generated from it: tests/golden/, tests/test_golden.py).  Independently:
+ *   (a) a second NumPy-float32 transcription (tests/np_greb.py),
+ *   (b) the property / known-answer / bug-compatibility tests listed in SURVEY.md section 4.
  *
  * Every function cites the reference file:line it follows (paths relative to the reference
  * root; "greb.f90" = src/greb.f90).  Arithmetic contract (reference Makefile:5-13 = gfortran

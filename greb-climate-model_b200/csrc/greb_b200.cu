@@ -578,6 +578,17 @@ extern "C" int greb_b200_get_fluxcorr(greb_b200_t h, int member, int which, floa
   return GREB_OK;
 }
 
+extern "C" int greb_b200_set_fluxcorr(greb_b200_t h, int member, int which, const float* in) {
+  if (!h) return GREB_E_INVALID;
+  if (!h->inited || member < 0 || member >= h->n_members || which < 0 || which > 2 || !in)
+    return fail(h, GREB_E_INVALID, "greb_b200_set_fluxcorr: bad arguments");
+  cudaSetDevice(h->device);
+  static const int sel[3] = {GC_TF, GC_QF, GC_TOF};  // ABI order: TF, qF, ToF
+  float* base = h->d_corr + (size_t)h->group_of[member] * GNT * GC_COUNT * GNC + (size_t)sel[which] * GNC;
+  CK(cudaMemcpy2D(base, (size_t)GC_COUNT * GNC * 4, in, GNC * 4, GNC * 4, GNT, cudaMemcpyHostToDevice));
+  return GREB_OK;
+}
+
 extern "C" int greb_b200_get_monthly(greb_b200_t h, int member, float* out) {
   if (!h) return GREB_E_INVALID;
   if (!h->inited || member < 0 || member >= h->n_members || !out)

@@ -26,7 +26,7 @@ ABI_SYMBOLS = ["greb_b200_physics_defaults", "greb_b200_physics_original", "greb
                "greb_b200_pad_co2", "greb_b200_init", "greb_b200_spinup", "greb_b200_reset_scenario",
                "greb_b200_run", "greb_b200_time_loop", "greb_b200_get_state", "greb_b200_set_state",
                "greb_b200_get_states", "greb_b200_set_states",
-               "greb_b200_get_fluxcorr", "greb_b200_get_monthly", "greb_b200_diag_device", "greb_b200_get_flags",
+               "greb_b200_get_fluxcorr", "greb_b200_set_fluxcorr", "greb_b200_get_monthly", "greb_b200_diag_device", "greb_b200_get_flags",
                "greb_b200_circulation", "greb_b200_last_kernel_ms"]
 
 
@@ -98,6 +98,7 @@ def load_library():
     L.greb_b200_get_states.argtypes = [vp, vp]
     L.greb_b200_set_states.argtypes = [vp, vp]
     L.greb_b200_get_fluxcorr.argtypes = [vp, C.c_int, C.c_int, fp]
+    L.greb_b200_set_fluxcorr.argtypes = [vp, C.c_int, C.c_int, fp]
     L.greb_b200_get_monthly.argtypes = [vp, C.c_int, fp]
     L.greb_b200_diag_device.argtypes = [vp, C.POINTER(vp), ip]
     L.greb_b200_get_flags.argtypes = [vp, ip]
@@ -250,6 +251,11 @@ class Ensemble:
         a = np.zeros((NT, YD, XD), dtype=np.float32)
         self._ck(self.L.greb_b200_get_fluxcorr(self.h, m, which, _p(a)), "greb_b200_get_fluxcorr")
         return a
+
+    def set_fluxcorr(self, m: int, which: int, a) -> None:
+        a = _f(a)
+        assert a.shape == (NT, YD, XD)
+        self._ck(self.L.greb_b200_set_fluxcorr(self.h, m, which, _p(a)), "greb_b200_set_fluxcorr")
 
     def get_monthly(self, m: int) -> np.ndarray:
         a = np.zeros((12, 5, YD, XD), dtype=np.float32)

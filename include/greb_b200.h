@@ -136,6 +136,10 @@ int greb_b200_get_states(greb_b200_t h, float* out);
 int greb_b200_set_states(greb_b200_t h, const float* in);
 /* which: 0 = TF_correct, 1 = qF_correct, 2 = ToF_correct (src/greb.f90:110), out [730][48][96] */
 int greb_b200_get_fluxcorr(greb_b200_t h, int member, int which, float* out);
+/* Restores flux corrections saved with greb_b200_get_fluxcorr (a spin-up cache: together with
+ * get/set_state it lets a later run skip qflux_correction, src/greb.f90:311-364).  The corrections
+ * belong to the member's physics group, i.e. to every member with identical physics_par. */
+int greb_b200_set_fluxcorr(greb_b200_t h, int member, int which, const float* in);
 /* last completed year's monthly means of one member: out[12][5][48][96] */
 int greb_b200_get_monthly(greb_b200_t h, int member, float* out);
 /* device-resident per-member diagnostics of the last completed year, 2 floats per member

@@ -313,3 +313,25 @@ def test_full_size_ensemble_properties(oracle_mod, forcing):
         out_o, gm_o = o.run(1, co2)
         check_monthly(out[i, 0], out_o[0], forcing.z_topo, o.physics, f"member {m}")
         assert abs(float(gm[m, 0]) - float(gm_o[0])) <= TOL_GM
+
+
+def test_spinup_cache_restores_a_run_bit_for_bit(forcing):
+    """flux corrections + state saved from one handle let another handle skip
+    qflux_correction and continue with identical results."""
+    p = product_physics(kappa=9.1e5, a_cloud=0.34)
+    e1 = make_ensemble(forcing, [p], [[560.0, 560.0]])
+    e1.spinup(1)
+    corr = [e1.get_fluxcorr(0, w) for w in range(3)]
+    state = {n: e1.get_state(0, n) for n in NAMES}
+    e1.reset_scenario()
+    out1, gm1, _ = e1.run(2)
+    e1.close()
+    e2 = make_ensemble(forcing, [p], [[560.0, 560.0]])       # no spin-up here
+    for w in range(3):
+        e2.set_fluxcorr(0, w, corr[w])
+    for n, a in state.items():
+        e2.set_state(0, n, a)
+    e2.reset_scenario()
+    out2, gm2, _ = e2.run(2)
+    assert np.array_equal(out1, out2) and np.array_equal(gm1, gm2)
+    e2.close()

@@ -52,18 +52,10 @@ NCU = {
 WORKLOAD = "configs[2]: 1024-member perturbed-parameter/CO2 ensemble per GPU, 96x48, synthetic S0 forcing"
 
 
-def member_physics(m: int, default_physics):
-    """SURVEY.md 8d config 3 draws."""
-    rng = np.random.default_rng(1000 + m)
-    p = default_physics()
-    co2 = float(rng.uniform(280.0, 1120.0))
-    p.kappa = float(rng.uniform(6e5, 1e6))
-    p.ct_sens *= float(rng.uniform(0.8, 1.2))
-    p.ce *= float(rng.uniform(0.8, 1.2))
-    p.co_turb *= float(rng.uniform(0.8, 1.2))
-    p.a_cloud += float(rng.uniform(-0.05, 0.05))
-    p.da_ice += float(rng.uniform(-0.05, 0.05))
-    return p, co2
+def member_physics(m: int, default_physics=None):
+    """SURVEY.md 8d config 3 draws (greb_b200/campaign.py)."""
+    from greb_b200 import campaign
+    return campaign.perturbed_member(m)
 
 
 # ------------------------------------------------------------------------------------------------

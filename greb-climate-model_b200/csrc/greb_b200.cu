@@ -6,6 +6,7 @@
 // There is NO CPU path in this file: every compute entry point needs an sm_100 device and fails
 // with GREB_E_NO_DEVICE otherwise.
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -34,7 +35,9 @@ __device__ __forceinline__ void cta_prologue(GrebMemberConst* dst, const GrebMem
 
 // One CTA integrates one ensemble member for a.nsteps 12-hour steps (time_loop, f:239-274, or
 // qflux_correction, f:325-362, selected by a.spinup).
-template <int MODE>
+// SW = 1: the build with the process switches of greb.original.model.f90 (GREB_SW_*), launched only
+// when a member of the handle has a switch set, so the default path carries none of that code.
+template <int MODE, int SW>
 __global__ void __launch_bounds__(GREB_NTHREADS, 1) greb_member_kernel(const GrebKernelArgs a) {
   extern __shared__ __align__(16) float smem[];
   __shared__ GrebMemberConst mc_s;
@@ -51,7 +54,7 @@ __global__ void __launch_bounds__(GREB_NTHREADS, 1) greb_member_kernel(const Gre
 #endif
   ctx.lane_u = threadIdx.x & 31;
   ctx.smem = smem;
-  member_run<MODE>(ctx, a, mc_s, member);
+  member_run<MODE, SW>(ctx, a, mc_s, member);
 }
 
 // circulation(X_in, dX_crcl, h_scl, wz) (f:528-553): one CTA per field
@@ -118,6 +121,7 @@ struct greb_b200_handle_s {
   std::vector<char> have_member;
   std::vector<std::vector<float>> co2;
   std::vector<int> year0;
+  std::vector<unsigned> switches;  // GREB_SW_* per member
   std::vector<int> group_of;   // member -> group
   std::vector<int> group_rep;  // group -> representative member
   int co2_stride = 0;
@@ -183,6 +187,7 @@ extern "C" int greb_b200_create(greb_b200_t* out, int n_members, int device) {
   h->have_member.assign(n_members, 0);
   h->co2.resize(n_members);
   h->year0.assign(n_members, 1940);
+  h->switches.assign(n_members, 0u);
   for (auto& p : h->phys) greb_b200_physics_defaults(&p);
   cudaSetDevice(device);
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -197,8 +202,10 @@ extern "C" int greb_b200_create(greb_b200_t* out, int n_members, int device) {
     cudaEventCreateWithFlags(&h->ev_k[i], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_c[i], cudaEventDisableTiming);
   }
-  cudaFuncSetAttribute(greb_member_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GREB_SMEM_BYTES);
-  cudaFuncSetAttribute(greb_member_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GREB_SMEM_BYTES);
+  cudaFuncSetAttribute(greb_member_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GREB_SMEM_BYTES);
+  cudaFuncSetAttribute(greb_member_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GREB_SMEM_BYTES);
+  cudaFuncSetAttribute(greb_member_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GREB_SMEM_BYTES);
+  cudaFuncSetAttribute(greb_member_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GREB_SMEM_BYTES);
   cudaFuncSetAttribute(greb_circulation_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GREB_SMEM_BYTES);
   cudaFuncSetAttribute(greb_circulation_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GREB_SMEM_BYTES);
   *out = h;
@@ -248,8 +255,13 @@ extern "C" int greb_b200_set_arithmetic(greb_b200_t h, int mode) {
 }
 
 static void launch_member(greb_b200_t h, int grid, const GrebKernelArgs& a) {
-  if (h->arith == GREB_ARITH_FAST) greb_member_kernel<1><<<grid, GREB_NTHREADS, GREB_SMEM_BYTES, h->stream>>>(a);
-  else greb_member_kernel<0><<<grid, GREB_NTHREADS, GREB_SMEM_BYTES, h->stream>>>(a);
+  bool sw = false;
+  for (unsigned m : h->switches) sw = sw || m != 0;
+  const bool fast = h->arith == GREB_ARITH_FAST;
+  if (!sw && fast) greb_member_kernel<1, 0><<<grid, GREB_NTHREADS, GREB_SMEM_BYTES, h->stream>>>(a);
+  else if (!sw) greb_member_kernel<0, 0><<<grid, GREB_NTHREADS, GREB_SMEM_BYTES, h->stream>>>(a);
+  else if (fast) greb_member_kernel<1, 1><<<grid, GREB_NTHREADS, GREB_SMEM_BYTES, h->stream>>>(a);
+  else greb_member_kernel<0, 1><<<grid, GREB_NTHREADS, GREB_SMEM_BYTES, h->stream>>>(a);
 }
 
 extern "C" int greb_b200_set_forcing(greb_b200_t h, const float* z_topo, const float* glacier, const float* sw_solar,
@@ -278,6 +290,30 @@ extern "C" int greb_b200_set_member(greb_b200_t h, int member, const greb_physic
   return GREB_OK;
 }
 
+// switches that change the spin-up (everything but the scenario-only SST forcing)
+static unsigned spinup_switches(unsigned mask) { return mask & ~(unsigned)GREB_SW_SST_PLUS_1K; }
+
+extern "C" int greb_b200_set_switches(greb_b200_t h, int member, unsigned mask) {
+  if (!h) return GREB_E_INVALID;
+  if (member < 0 || member >= h->n_members || (mask & ~(unsigned)GREB_SW_ALL))
+    return fail(h, GREB_E_INVALID, "greb_b200_set_switches: bad member index or unknown switch bits");
+  if (h->inited) {
+    // only the scenario-only bit may change once the spin-up groups exist
+    if (spinup_switches(mask) != spinup_switches(h->switches[member]))
+      return fail(h, GREB_E_INVALID,
+                  "greb_b200_set_switches: after greb_b200_init only GREB_SW_SST_PLUS_1K may be toggled");
+    h->switches[member] = mask;
+    cudaSetDevice(h->device);
+    const int sw = (int)mask;
+    CK(cudaMemcpyAsync(reinterpret_cast<char*>(h->d_mc + member) + offsetof(GrebMemberConst, switches), &sw,
+                       sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return GREB_OK;
+  }
+  h->switches[member] = mask;
+  return GREB_OK;
+}
+
 template <class T>
 static cudaError_t upload(T** dptr, const std::vector<T>& v) {
   cudaError_t e = cudaMalloc((void**)dptr, v.size() * sizeof(T));
@@ -298,7 +334,8 @@ extern "C" int greb_b200_init(greb_b200_t h) {
     int g = -1;
     // compare against group representatives (linear scan with a cheap hash of the bytes)
     for (int gi = (int)h->group_rep.size() - 1; gi >= 0; --gi)
-      if (greb_physics_equal(h->phys[m], h->phys[h->group_rep[gi]])) {
+      if (greb_physics_equal(h->phys[m], h->phys[h->group_rep[gi]]) &&
+          spinup_switches(h->switches[m]) == spinup_switches(h->switches[h->group_rep[gi]])) {
         g = gi;
         break;
       }
@@ -344,6 +381,7 @@ extern "C" int greb_b200_init(greb_b200_t h) {
       memcpy(&state[(size_t)m * GS_COUNT * GNC], &state[(size_t)r * GS_COUNT * GNC], GS_COUNT * GNC * 4);
     }
   }
+  for (int m = 0; m < N; ++m) mc[m].switches = (int)h->switches[m];
   h->co2_stride = 1;
   for (int m = 0; m < N; ++m) h->co2_stride = std::max(h->co2_stride, (int)h->co2[m].size());
   std::vector<float> co2((size_t)N * h->co2_stride, 680.f);

@@ -27,6 +27,7 @@
 
 #include "greb_simt.h"
 #include "greb_types.h"
+#include "../../include/greb_b200.h"  // GREB_SW_*
 
 #define GREB_DT 43200.0f  // f:38  (integer dt in real expressions)
 
@@ -824,7 +825,7 @@ struct StepInfo {
 // flux corrections in spin-up mode; stashes the air-temperature and humidity tendencies.
 // MODE 1 (GREB_ARITH_FAST): approximate division and transcendentals (2 ulp); MODE 0: IEEE division and
 // the CUDA libm, like the reference's true divisions
-template <int MODE>
+template <int MODE, int SW>
 GDEV void column_phase_a(const GrebKernelArgs& a, const GrebMemberConst& mc, int member, const StepInfo& si, int k,
                          vi idx0, float* stash) {
 #define DIVF(x, y) (MODE == 1 ? v_div_fast((x), (y)) : (x) / (y))
@@ -866,6 +867,18 @@ GDEV void column_phase_a(const GrebKernelArgs& a, const GrebMemberConst& mc, int
     v_ldg4(c2, a.toclim, idx0);
   }
   v_ld4(tsmn4, acc + GA_TSMN * GNC, idx0);
+  // process switches (greb.original.model.f90 log_exp experiments); sw == 0 is the full model
+  const int sw_ = SW ? mc.switches : 0;  // SW == 0: the switch code is compiled out
+  vf qcl4[4];
+  if (sw_ & GREB_SW_LINEAR_VAPOR_EMISSIVITY) v_ldg4(qcl4, a.qclim + (size_t)si.ityr * GNC, idx0);
+  if ((sw_ & GREB_SW_SST_PLUS_1K) && !si.spinup) {
+    // orig:226 runs BEFORE time_loop updates the module variable ityr (orig:248), so the SST comes
+    // from the climatology of the PREVIOUS step (step 730 for the first step of a year)
+    vf tcl[4];
+    v_ldg4(tcl, a.tclim + (size_t)((si.ityr + GNT - 1) % GNT) * GNC, idx0);
+    GUNROLL
+    for (int i = 0; i < 4; ++i) Ts4[i] = v_sel(v_bit(mask4[i], 1), tcl[i] + 1.0f, Ts4[i]);
+  }
 
   vf Ts0o[4], To0o[4], capo4[4], tendA4[4], tq4[4], tfo[4], tofo[4], albo[4];
   GUNROLL
@@ -884,15 +897,19 @@ GDEV void column_phase_a(const GrebKernelArgs& a, const GrebMemberConst& mc, int
     a_surf = v_sel(Ts <= T1, v_bcast(a_ice), a_surf);
     a_surf = v_sel(Ts >= T2, v_bcast(mc.a_no_ice), a_surf);
     a_surf = v_sel(glac, v_bcast(a_ice), a_surf);
+    if (sw_ & GREB_SW_NO_ICE_ALBEDO) a_surf = v_bcast(mc.a_no_ice);  // orig:394
     const vf albedo = a_surf + a_atmos - a_surf * a_atmos;
     const vf sw = solar * (1.0f - albedo);
 
     // ---- LWradiation, f:420-432
     const vf e_co2 = ez * si.co2;
-    const vf e_vapor = ez * mc.r_qviwv * q;
+    vf e_vapor = ez * mc.r_qviwv * q;
+    if (sw_ & GREB_SW_LINEAR_VAPOR_EMISSIVITY) e_vapor = ez * mc.r_qviwv * qcl4[i];  // orig:423
     vf em = pe[3] * LOGF(pe[0] * e_co2 + pe[1] * e_vapor + pe[2]) + pe[6] + pe[4] * LOGF(pe[0] * e_co2 + pe[2]) +
             pe[5] * LOGF(pe[1] * e_vapor + pe[2]);
     em = DIVF(pe[7] - cld, v_bcast(pe[8])) * (em - pe[9]) + pe[9];
+    if (sw_ & GREB_SW_LINEAR_VAPOR_EMISSIVITY)
+      em = em + ((0.022f / (0.15f * 24.f)) * mc.r_qviwv) * (q - qcl4[i]);  // orig:430
     const vf LWsurf = -(mc.sig * pow4(Ts));
     const vf LWdown = -(em * mc.sig * pow4(Ta + dTrad));
     const vf LWup = LWdown;
@@ -903,10 +920,16 @@ GDEV void column_phase_a(const GrebKernelArgs& a, const GrebMemberConst& mc, int
     // ---- hydro, f:457-467 (abswind incl. gustiness is precomputed on the host, f:452-454)
     vf qs = 3.75e-3f * EXPF(DIVF(17.08085f * (Ts - 273.15f), Ts - 273.15f + 234.175f));
     qs = qs * ez;
-    const vf Qlat = (q - qs) * absw * mc.cq_latent * mc.rho_air * mc.ce * swet;
-    const vf dq_eva = -(DIVF(DIVF(Qlat, v_bcast(mc.cq_latent)), v_bcast(mc.r_qviwv)));
-    const vf dq_rain = mc.cq_rain * q;
-    const vf Qlat_air = -(dq_rain * mc.cq_latent * mc.r_qviwv);
+    vf Qlat = (q - qs) * absw * mc.cq_latent * mc.rho_air * mc.ce * swet;
+    vf dq_eva = -(DIVF(DIVF(Qlat, v_bcast(mc.cq_latent)), v_bcast(mc.r_qviwv)));
+    vf dq_rain = mc.cq_rain * q;
+    vf Qlat_air = -(dq_rain * mc.cq_latent * mc.r_qviwv);
+    if (sw_ & GREB_SW_NO_HYDRO) {  // orig:452-453
+      Qlat = v_bcast(0.0f);
+      dq_eva = v_bcast(0.0f);
+      dq_rain = v_bcast(0.0f);
+      Qlat_air = v_bcast(0.0f);
+    }
 
     // ---- deep_ocean, f:505-523
     const vb warm = ocean && (Ts >= mc.To_ice2);
@@ -917,6 +940,10 @@ GDEV void column_phase_a(const GrebKernelArgs& a, const GrebMemberConst& mc, int
     const vf Tx = v_max(v_bcast(mc.To_ice2), Ts);
     dTo = dTo + DIVF(GREB_DT * mc.co_turb * (Tx - To), mc.cap_ocean * (zoc - mld));
     dToc = dToc + DIVF(GREB_DT * mc.co_turb * (To - Tx), mc.cap_ocean * mld);
+    if (sw_ & GREB_SW_NO_DEEP_OCEAN) {  // orig:513-515
+      dTo = v_bcast(0.0f);
+      dToc = v_bcast(0.0f);
+    }
 
     vf Ts0, To0;
     tendA4[i] = DIVF(GREB_DT * (LWup + LWdown - em * LWsurf + Qlat_air - Qsens), v_bcast(mc.cap_air));  // f:260 / f:336
@@ -947,6 +974,10 @@ GDEV void column_phase_a(const GrebKernelArgs& a, const GrebMemberConst& mc, int
       ramp = v_sel(Ts0 <= mc.To_ice1, v_bcast(mc.cap_land), ramp);
       ramp = v_sel(Ts0 >= mc.To_ice2, capo, ramp);
       capn = v_sel(ocean, ramp, capn);
+      if (sw_ & GREB_SW_NO_ICE_ALBEDO) {  // orig:492-495
+        capn = v_sel(v_bit(mask4[i], 3), v_bcast(mc.cap_land), capn);
+        capn = v_sel(ocean, capo, capn);
+      }
       capn = v_sel(glac, v_bcast(mc.cap_land), capn);
     }
     Ts0o[i] = Ts0;
@@ -1083,7 +1114,7 @@ GDEV StepInfo step_info(const GrebKernelArgs& a, const GrebMemberConst& mc, int 
 // `smem` layout: greb_types.h GSM_*.  The SplitBar and the flags must have been initialised
 // (sb_init with the number of arriving units, flags = 0) before the first call.
 // =============================================================================================
-template <int MODE = 0>
+template <int MODE = 0, int SW = 0>
 GDEV void member_run_main(const SimtCtx& ctx, const GrebKernelArgs& a, const GrebMemberConst& mc, int member,
                           SyncState& ss) {
   float* smem = ctx.smem;
@@ -1112,7 +1143,7 @@ GDEV void member_run_main(const SimtCtx& ctx, const GrebKernelArgs& a, const Gre
 #endif
     // ---- phase A: column physics, Ts/To/cap update
     GNOUNROLL
-    for (int q = 0; q < 3; ++q) column_phase_a<MODE>(a, mc, member, si, g.k, g.k * GX + g.col + 4 * q, stash);
+    for (int q = 0; q < 3; ++q) column_phase_a<MODE, SW>(a, mc, member, si, g.k, g.k * GX + g.col + 4 * q, stash);
     SCLK(0)
     {
       const FastRow fr = fast_row(g.k, mc);
@@ -1126,6 +1157,9 @@ GDEV void member_run_main(const SimtCtx& ctx, const GrebKernelArgs& a, const Gre
     // ---- circulation of air temperature (f:301), then of humidity (f:303): one code instance
     GNOUNROLL
     for (int fld = 0; fld < 2; ++fld) {
+      // orig:560-564: with zero winds every advection term is +-0, so X + dx_diffuse + dx_advec == X + dx_diffuse
+      if (SW && fld == 1 && (mc.switches & GREB_SW_VAPOR_DIFFUSION_ONLY))
+        tile_load_uv(t, g, forc + GF_U * GNC, forc + GF_V * GNC, smem, 0.0f, 0.0f, 0.0f);
       tile_load_wz(t, g, wzg + fld * GNC, smem);
       tile_load_field(t, g, st + (fld == 0 ? GS_TA : GS_Q) * GNC);
       SCLK(2)
@@ -1186,7 +1220,7 @@ GDEV void member_run_main(const SimtCtx& ctx, const GrebKernelArgs& a, const Gre
 }
 
 // the helper warps' view of the same step sequence (identical barrier pattern)
-template <int MODE = 0>
+template <int MODE = 0, int SW = 0>
 GDEV void member_run_helper(const SimtCtx& ctx, const GrebKernelArgs& a, const GrebMemberConst& mc, int member,
                             SyncState& ss) {
   const float* st = a.state + (size_t)member * GS_COUNT * GNC;
@@ -1201,6 +1235,15 @@ GDEV void member_run_helper(const SimtCtx& ctx, const GrebKernelArgs& a, const G
     cta_sync(ctx);
     GNOUNROLL
     for (int fld = 0; fld < 2; ++fld) {
+      if (SW && fld == 1 && (mc.switches & GREB_SW_VAPOR_DIFFUSION_ONLY)) {
+        GUNROLL
+        for (int i = 0; i < GREB_HROWS; ++i)
+          GUNROLL
+          for (int c = 0; c < 3; ++c) {
+            hr[i].U[c] = v_bcast(0.0f);
+            hr[i].V[c] = v_bcast(0.0f);
+          }
+      }
       helper_load_wz(hr, hg, wzg + fld * GNC);
       circulation_helper<MODE>(ctx, hr, hg, mc, st + (fld == 0 ? GS_TA : GS_Q) * GNC, ss);
     }
@@ -1212,13 +1255,13 @@ GDEV void member_run_helper(const SimtCtx& ctx, const GrebKernelArgs& a, const G
   }
 }
 
-template <int MODE = 0>
+template <int MODE = 0, int SW = 0>
 GDEV void member_run(const SimtCtx& ctx, const GrebKernelArgs& a, const GrebMemberConst& mc, int member) {
   SyncState ss;
   ss.bar = reinterpret_cast<SplitBar*>(ctx.smem + GSM_SYNC);
   ss.hb = ctx.smem + GSM_HB;
   ss.smem = ctx.smem;
   ss.phase = 0;
-  if (ctx_is_helper(ctx)) member_run_helper<MODE>(ctx, a, mc, member, ss);
-  else member_run_main<MODE>(ctx, a, mc, member, ss);
+  if (ctx_is_helper(ctx)) member_run_helper<MODE, SW>(ctx, a, mc, member, ss);
+  else member_run_main<MODE, SW>(ctx, a, mc, member, ss);
 }

@@ -78,6 +78,7 @@ void greb_build_forcing(GrebHostForcing& F, const float* z_topo, const float* gl
     if (z_topo[c] >= 0.f) m |= GM_TOPO_GE0;  // f:384
     if (z_topo[c] < 0.f) m |= GM_TOPO_LT0;   // f:389, 483, 511
     if (glacier[c] > 0.5f) m |= GM_GLACIER;  // f:395, 490
+    if (z_topo[c] > 0.f) m |= GM_TOPO_GT0;   // greb.original.model.f90:493 (log_exp <= 5)
     F.mask[c] = m;
     // f:1087-1094 Toclim
     float mn = tclim[c];

@@ -36,7 +36,7 @@ enum { GS_TS = 0, GS_TA, GS_TO, GS_Q, GS_CAP, GS_COUNT };
 // acc[member][GA_*][GNC]: the five monthly accumulators (:149) + annual Tsurf accumulator tsmn (:145)
 enum { GA_TMM = 0, GA_TAMM, GA_TOMM, GA_QMM, GA_APMM, GA_TSMN, GA_COUNT };
 // static mask bits (the reference's three different land/ocean predicates)
-enum { GM_TOPO_GE0 = 1, GM_TOPO_LT0 = 2, GM_GLACIER = 4 };
+enum { GM_TOPO_GE0 = 1, GM_TOPO_LT0 = 2, GM_GLACIER = 4, GM_TOPO_GT0 = 8 };
 
 struct GrebMemberConst {
   // physics scalars used on the device (namelist physics_par, src/greb.f90:68-104)
@@ -58,7 +58,8 @@ struct GrebMemberConst {
   int helper_row[GREB_MAXH];
   int n_hslots;
   int group;  // physics group (shares wz fields and flux corrections)
-  int pad_[2];
+  int switches;  // GREB_SW_* process switches (include/greb_b200.h), 0 = the full model
+  int pad_[1];
 };
 
 struct GrebKernelArgs {

@@ -60,6 +60,12 @@ module greb_b200_c
        type(greb_physics_par), intent(in) :: p
        real(c_float), intent(in) :: co2_ppm(*)
      end function
+     ! process switches = the log_exp experiments of greb.original.model.f90 (GREB_SW_* bit mask)
+     integer(c_int) function greb_b200_set_switches(h, member, mask) bind(C, name='greb_b200_set_switches')
+       import :: c_ptr, c_int
+       type(c_ptr), value :: h
+       integer(c_int), value :: member, mask
+     end function
      integer(c_int) function greb_b200_init(h) bind(C, name='greb_b200_init')
        import :: c_ptr, c_int
        type(c_ptr), value :: h

@@ -346,3 +346,123 @@ def run_namelists(namelists: Sequence[str], input_dir: str = "input", workdir: s
         return results
     finally:
         ens.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# greb.original.model.f90: the `log_exp` sensitivity experiments (namelist_original)
+# ------------------------------------------------------------------------------------------------
+# log_exp -> process switches of include/greb_b200.h.  The original model accumulates its switches
+# with `log_exp <= k` tests, so experiment L switches off everything of the experiments above it.
+# log_exp <= 4, 7 and 16 are NOT reproducible: `circulation` returns before assigning its
+# intent(out) result (orig:553-555) and time_loop adds uninitialised stack arrays.
+_SW = _lib
+ORIGINAL_EXPERIMENTS = {
+    5: _SW.SW_NO_ICE_ALBEDO | _SW.SW_NO_HYDRO | _SW.SW_NO_DEEP_OCEAN,       # orig:394, 453, 492, 514 (+ mld = d_ocean :165)
+    6: _SW.SW_NO_HYDRO | _SW.SW_NO_DEEP_OCEAN,                               # orig:453, 514
+    8: _SW.SW_VAPOR_DIFFUSION_ONLY | _SW.SW_NO_DEEP_OCEAN,                   # orig:560-564, 514
+    9: _SW.SW_NO_DEEP_OCEAN,                                                 # orig:165, 514
+    10: 0,                                                                   # the full model
+    11: _SW.SW_LINEAR_VAPOR_EMISSIVITY | _SW.SW_NO_DEEP_OCEAN,               # orig:166, 423, 430, 514
+    12: 0,                                                                   # A1B CO2 pathway, orig:179, 946-951
+    13: _SW.SW_NO_HYDRO,                                                     # A1B without hydro, orig:453
+    14: _SW.SW_SST_PLUS_1K | _SW.SW_NO_DEEP_OCEAN,                           # orig:225-226, 515
+    15: _SW.SW_SST_PLUS_1K | _SW.SW_NO_DEEP_OCEAN | _SW.SW_NO_HYDRO,         # + orig:453
+}
+
+
+def a1b_co2(year: float) -> np.float32:
+    """co2_level of greb.original.model.f90:945-951 for log_exp 12/13 (fp32, `year` is a real)."""
+    y = np.float32(year)
+    co2 = np.float32(680.0)
+    if y <= np.float32(2000.0):
+        co2 = np.float32(310.0) + np.float32(np.float32(60.0) / np.float32(50.0)) * (y - np.float32(1950.0))
+    if np.float32(2000.0) < y <= np.float32(2050.0):
+        co2 = np.float32(370.0) + np.float32(np.float32(150.0) / np.float32(50.0)) * (y - np.float32(2000.0))
+    if np.float32(2050.0) < y <= np.float32(2100.0):
+        co2 = np.float32(520.0) + np.float32(np.float32(180.0) / np.float32(50.0)) * (y - np.float32(2050.0))
+    return np.float32(co2)
+
+
+def original_experiment(log_exp: int, forcing: "synth.Forcing", time_scnr: int, d_ocean: float = 50.0) -> dict:
+    """What `log_exp` of greb.original.model.f90 means for the C ABI: the switch mask, the modified
+    inputs (orig:162-166), CO2_ctrl (orig:178-179) and the scenario CO2 path (orig:225, 939-951;
+    the scenario starts in 1940, orig:219)."""
+    if log_exp not in ORIGINAL_EXPERIMENTS:
+        raise ValueError(f"log_exp = {log_exp}: the reference leaves circulation's result undefined "
+                         "(greb.original.model.f90:553-555); reproducible experiments: "
+                         f"{sorted(ORIGINAL_EXPERIMENTS)}")
+    f = forcing
+    if log_exp <= 9 or log_exp == 11:                                # orig:165-166 "no deep ocean"
+        f = dataclasses.replace(f, mldclim=np.full_like(f.mldclim, np.float32(d_ocean)))
+    co2_ctrl = 298.0 if log_exp in (12, 13) else 340.0
+    if log_exp in (12, 13):
+        path = np.array([a1b_co2(1940 + y) for y in range(time_scnr)], dtype=np.float32)
+    elif 14 <= log_exp <= 16:
+        path = np.full(time_scnr, co2_ctrl, dtype=np.float32)        # orig:225
+    else:
+        path = np.full(time_scnr, 680.0, dtype=np.float32)           # orig:943
+    return {"switches": ORIGINAL_EXPERIMENTS[log_exp], "forcing": f, "co2_ctrl": co2_ctrl, "co2_scenario": path}
+
+
+def run_original(log_exp: int, forcing: "synth.Forcing", time_flux: int = 3, time_ctrl: int = 3, time_scnr: int = 50,
+                 device: int = 0, arith: str = "exact") -> dict:
+    """greb.original.model.f90:138-233 through the C ABI: flux-correction spin-up and control run
+    at CO2_ctrl, then the scenario from the same initial fields (cap_surf carries over, orig:219).
+    Returns the record streams of units 21 and 22 as [years][12][5][48][96] plus the annual means."""
+    ex = original_experiment(log_exp, forcing, time_scnr)
+    ens = _lib.Ensemble(1, device=device)
+    try:
+        ens.set_arithmetic(arith)
+        ens.set_forcing(ex["forcing"])
+        p = _lib.original_physics()
+        p.co2_flux = ex["co2_ctrl"]
+        co2 = np.concatenate([np.full(time_ctrl, ex["co2_ctrl"], dtype=np.float32), ex["co2_scenario"]])
+        ens.set_member(0, p, co2 if len(co2) else [680.0], year0=1970)
+        ens.set_switches(0, ex["switches"] & ~_lib.SW_SST_PLUS_1K)   # orig:226 applies to the scenario only
+        ens.init()
+        ens.spinup(time_flux)                                        # orig:201
+        tf = ens.get_fluxcorr(0, 0)                                  # orig:204-206
+        ini = {n: ens.get_state(0, n) for n in ("Ts", "Ta", "To", "q")}
+        ens.reset_scenario()
+        ctrl, gmc, _ = ens.run(time_ctrl)                            # orig:209-215
+        for n, a in ini.items():                                     # orig:219
+            ens.set_state(0, n, a)
+        ens.set_switches(0, ex["switches"])
+        scen, gm, gmw = ens.run(time_scnr)                           # orig:220-231
+        return {"control": ctrl[0], "scenario": scen[0], "gmean_control": gmc[0], "gmean": gm[0],
+                "gmean_coslat": gmw[0], "tf_correct": tf, "flags": ens.flags(), "experiment": ex}
+    finally:
+        ens.close()
+
+
+def write_control(path: str, tf_correct: np.ndarray, control_monthly: np.ndarray) -> None:
+    """`output/control` of greb.original.model.f90: 730 records of TF_correct (orig:204-206), then the
+    control run's monthly means written over them from record 1 (orig:209-215, unit 21)."""
+    recs = np.ascontiguousarray(tf_correct, dtype="<f4").reshape(-1, YD, XD)
+    mon = np.ascontiguousarray(control_monthly, dtype="<f4").reshape(-1, YD, XD)
+    n = max(len(recs), len(mon))
+    out = np.zeros((n, YD, XD), dtype="<f4")
+    out[:len(recs)] = recs
+    out[:len(mon)] = mon
+    os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+    out.tofile(path)
+
+
+def run_original_namelist(namelist: str = "namelist_original", input_dir: str = "input", workdir: str = ".",
+                          device: int = 0, arith: str = "exact", write_files: bool = True) -> dict:
+    """`./greb_original` work-alike (greb.original.shell.web-public.f90:16-60): reads the NUMERICS and
+    PHYSICS groups of `namelist_original` and the ten input files, runs spin-up, control and
+    scenario on the GPU and writes `output/control` and `output/scenario`."""
+    with open(namelist) as fh:
+        groups = parse_namelist(fh.read())
+    num = {k.lower(): v for k, v in groups.get("numerics", {}).items()}
+    phy = {k.lower(): v for k, v in groups.get("physics", {}).items()}
+    tf = int(num.get("time_flux", [0])[0])
+    tc = int(num.get("time_ctrl", [0])[0])
+    ts = int(num.get("time_scnr", [0])[0])
+    log_exp = int(phy.get("log_exp", [0])[0])                       # orig:60 default 0
+    r = run_original(log_exp, read_inputs(input_dir), tf, tc, ts, device=device, arith=arith)
+    if write_files:
+        write_control(os.path.join(workdir, "output", "control"), r["tf_correct"], r["control"])
+        write_output(os.path.join(workdir, "output", "scenario"), r["scenario"])
+    return r

@@ -22,7 +22,7 @@ PHYS_FIELDS = ["pi", "sig", "rho_ocean", "rho_land", "rho_air", "cp_ocean", "cp_
 
 # every symbol include/greb_b200.h declares
 ABI_SYMBOLS = ["greb_b200_physics_defaults", "greb_b200_physics_original", "greb_b200_create", "greb_b200_destroy",
-               "greb_b200_last_error", "greb_b200_n_members", "greb_b200_set_arithmetic", "greb_b200_set_forcing", "greb_b200_set_member",
+               "greb_b200_last_error", "greb_b200_n_members", "greb_b200_set_arithmetic", "greb_b200_set_forcing", "greb_b200_set_member", "greb_b200_set_switches",
                "greb_b200_pad_co2", "greb_b200_init", "greb_b200_spinup", "greb_b200_reset_scenario",
                "greb_b200_run", "greb_b200_time_loop", "greb_b200_get_state", "greb_b200_set_state",
                "greb_b200_get_states", "greb_b200_set_states",
@@ -86,6 +86,7 @@ def load_library():
     L.greb_b200_set_arithmetic.argtypes = [vp, C.c_int]
     L.greb_b200_set_forcing.argtypes = [vp] + [fp] * 10
     L.greb_b200_set_member.argtypes = [vp, C.c_int, C.POINTER(Physics), fp, C.c_int, C.c_int]
+    L.greb_b200_set_switches.argtypes = [vp, C.c_int, C.c_uint]
     L.greb_b200_pad_co2.argtypes = [fp, C.c_int, fp, C.c_int]
     L.greb_b200_pad_co2.restype = None
     L.greb_b200_init.argtypes = [vp]
@@ -137,6 +138,9 @@ def _f(a):
 
 
 STATE = {"Ts": 0, "Ta": 1, "To": 2, "q": 3, "cap_surf": 4}
+# include/greb_b200.h GREB_SW_*: process switches (greb.original.model.f90 log_exp experiments)
+SW_NO_ICE_ALBEDO, SW_NO_HYDRO, SW_NO_DEEP_OCEAN, SW_VAPOR_DIFFUSION_ONLY, SW_LINEAR_VAPOR_EMISSIVITY, \
+    SW_SST_PLUS_1K = 1, 2, 4, 8, 16, 32
 
 
 class Ensemble:
@@ -185,6 +189,10 @@ class Ensemble:
         co2 = _f(np.atleast_1d(co2_ppm))
         self._ck(self.L.greb_b200_set_member(self.h, m, C.byref(physics), _p(co2), len(co2), year0),
                  "greb_b200_set_member")
+
+    def set_switches(self, m: int, mask: int):
+        """GREB_SW_* process switches of member m (include/greb_b200.h)."""
+        self._ck(self.L.greb_b200_set_switches(self.h, m, mask), "greb_b200_set_switches")
 
     def init(self):
         self._ck(self.L.greb_b200_init(self.h), "greb_b200_init")

@@ -96,6 +96,29 @@ int greb_b200_set_forcing(greb_b200_t h, const float* z_topo /*[48][96]*/, const
  * Members with identical physics share one flux-correction spin-up. */
 int greb_b200_set_member(greb_b200_t h, int member, const greb_physics_par* p, const float* co2_ppm, int n_years,
                          int year0);
+/* Process switches of one member: the well-defined sensitivity experiments of
+ * src/greb.original.model.f90 (`log_exp`, :60) as a bit mask; 0 (default) is the full model =
+ * log_exp 10 = src/greb.f90.  INTEGRATION.md lists the mask + input changes of every log_exp.
+ *   NO_ICE_ALBEDO      a_surf = a_no_ice (:394) and cap_surf without the sea-ice ramp (:492-495)
+ *   NO_HYDRO           hydro returns zeros (:452-453)
+ *   NO_DEEP_OCEAN      deep_ocean returns zeros (:513-515)
+ *   VAPOR_DIFFUSION_ONLY  circulation of q without advection (:560-564)
+ *   LINEAR_VAPOR_EMISSIVITY  e_vapor from qclim + linear term in em (:423, :430)
+ *   SST_PLUS_1K        scenario only: Ts1 = Tclim(:,:,ityr) + 1 where z_topo < 0 before every step (:226;
+ *                      ityr there still is the PREVIOUS step's, :248 updates it afterwards)
+ * Members with different masks never share a spin-up.  All bits but SST_PLUS_1K must be set
+ * before greb_b200_init; SST_PLUS_1K may be toggled between runs (control run without, scenario
+ * with). */
+enum {
+  GREB_SW_NO_ICE_ALBEDO = 1,
+  GREB_SW_NO_HYDRO = 2,
+  GREB_SW_NO_DEEP_OCEAN = 4,
+  GREB_SW_VAPOR_DIFFUSION_ONLY = 8,
+  GREB_SW_LINEAR_VAPOR_EMISSIVITY = 16,
+  GREB_SW_SST_PLUS_1K = 32,
+  GREB_SW_ALL = 63
+};
+int greb_b200_set_switches(greb_b200_t h, int member, unsigned mask);
 /* src/greb.f90:1047-1061: `n_given` values followed by padding to n_years (first<0 -> 680). */
 void greb_b200_pad_co2(const float* given, int n_given, float* co2_ppm, int n_years);
 

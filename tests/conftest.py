@@ -11,6 +11,20 @@ for p in (ROOT, PKG, os.path.join(ROOT, "tests")):
         sys.path.insert(0, p)
 
 
+def pytest_sessionstart(session):
+    """Keep the in-tree CUDA library in step with its sources (make is a no-op when it is): a stale
+    libgreb_b200.so would test yesterday's kernels.  Never fatal here — the ABI tests fail loudly if
+    the library is missing."""
+    import shutil
+    import subprocess
+    if os.environ.get("GREB_B200_LIB") or shutil.which("nvcc") is None or shutil.which("make") is None:
+        return
+    r = subprocess.run(["make", "-C", os.path.join(PKG, "csrc")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                       text=True)
+    if r.returncode != 0:
+        print("conftest: rebuilding libgreb_b200.so failed:\n" + r.stdout[-2000:])
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
     config.addinivalue_line("markers", "slow: long-running")

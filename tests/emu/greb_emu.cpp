@@ -40,7 +40,8 @@ struct WarpTask {
 void* warp_main(void* p) {
   WarpTask* t = (WarpTask*)p;
   if (t->ka) {
-    member_run(t->ctx, *t->ka, *t->mc, 0);
+    if (t->mc->switches) member_run<0, 1>(t->ctx, *t->ka, *t->mc, 0);
+    else member_run<0, 0>(t->ctx, *t->ka, *t->mc, 0);
   } else {
     const GrebCirculationArgs& a = *t->ca;
     const GrebMemberConst& mc = *t->mc;
@@ -185,6 +186,7 @@ int emu_steps(void* h, int it0, int nsteps, int spinup, float* out, int out_mont
   return 0;
 }
 
+void emu_set_switches(void* h, unsigned mask) { ((Emu*)h)->mc.switches = (int)mask; }
 void emu_reset_scenario(void* h) {
   Emu* e = (Emu*)h;
   std::fill(e->acc.begin(), e->acc.end(), 0.f);

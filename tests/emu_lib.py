@@ -39,6 +39,7 @@ def lib():
         L.emu_destroy.argtypes = [C.c_void_p]
         L.emu_steps.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, fp, C.c_int]
         L.emu_reset_scenario.argtypes = [C.c_void_p]
+        L.emu_set_switches.argtypes = [C.c_void_p, C.c_uint]
         L.emu_get_state.argtypes = [C.c_void_p, C.c_int, fp]
         L.emu_set_state.argtypes = [C.c_void_p, C.c_int, fp]
         L.emu_get_corr.argtypes = [C.c_void_p, fp]
@@ -91,6 +92,9 @@ class Emu:
 
     def reset_scenario(self):
         lib().emu_reset_scenario(self.h)
+
+    def set_switches(self, mask):
+        lib().emu_set_switches(self.h, mask)
 
     def get(self, which):
         a = np.zeros((YD, XD), dtype=np.float32)

@@ -1,0 +1,174 @@
+"""Big-grid circulation path (include/greb_grid.h; BASELINE.json configs[4]).
+
+One member on a grid too large for one SM (1440x720) is cut into latitude bands, one band per GPU /
+process; longitude stays whole, so the periodic wrap and the polar sub-sub-steps are GPU-local.  A
+sub-step needs rows k-2..k+2 (src/greb.f90:587-590, 771-780): every `s` sub-steps the ranks exchange
+2*s rows with each neighbour and then advance `s` sub-steps without communication, recomputing the
+shrinking halo redundantly (communication-avoiding halo).  The poles are not neighbours (no
+cross-pole term, f:589-590, 756-762, 789-795), so the band chain is open-ended.
+
+`DeviceBand` is the product (CUDA, libgreb_grid.so, fails loudly without it).  The exchange logic
+(`advance`) only needs an object with `substeps / rows / halo_refreshed`, which lets the tests drive
+it on the CPU over gloo with a stand-in band built on the parity oracle.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Tuple
+
+import numpy as np
+
+from . import lib as _lib
+from . import sharding
+
+GRID_SYMBOLS = ["greb_grid_create", "greb_grid_destroy", "greb_grid_last_error", "greb_grid_set_geometry",
+                "greb_grid_set_fields", "greb_grid_substeps", "greb_grid_view", "greb_grid_halo_refreshed",
+                "greb_grid_get", "greb_grid_last_ms"]
+_grid = None
+
+
+def grid_library_path() -> str:
+    return os.environ.get("GREB_GRID_LIB") or os.path.join(_lib.PKG_DIR, "libgreb_grid.so")
+
+
+def load_grid_library():
+    global _grid
+    if _grid is not None:
+        return _grid
+    path = grid_library_path()
+    if not os.path.exists(path):
+        raise _lib.GrebError(f"{path} is missing: build it with make -C {_lib.CSRC} (there is no CPU fallback)")
+    L = C.CDLL(path)
+    vp, fp, ip = C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int)
+    L.greb_grid_create.argtypes = [C.POINTER(vp)] + [C.c_int] * 6
+    L.greb_grid_destroy.argtypes = [vp]
+    L.greb_grid_last_error.argtypes = [vp]
+    L.greb_grid_last_error.restype = C.c_char_p
+    L.greb_grid_set_geometry.argtypes = [vp, C.c_float, C.c_float, ip, fp]
+    L.greb_grid_set_fields.argtypes = [vp, fp, fp, fp, fp]
+    L.greb_grid_substeps.argtypes = [vp, C.c_int]
+    L.greb_grid_view.argtypes = [vp, C.POINTER(vp), ip, ip, ip, ip]
+    L.greb_grid_halo_refreshed.argtypes = [vp]
+    L.greb_grid_get.argtypes = [vp, fp]
+    L.greb_grid_last_ms.argtypes = [vp, fp, ip]
+    _grid = L
+    return L
+
+
+def band_range(ny: int, world: int, rank: int) -> Tuple[int, int]:
+    """latitude rows [k0, k1) of `rank`: contiguous bands, heights differ by at most one"""
+    return sharding.shard_range(ny, world, rank)
+
+
+class DeviceBand:
+    """one latitude band of one member on one B200 (a handle of include/greb_grid.h)"""
+
+    def __init__(self, nx: int, ny: int, k0: int, k1: int, s: int, device: int = 0, pi: float = 3.1416,
+                 kappa: float = 8e5):
+        self.L = load_grid_library()
+        self.h = C.c_void_p()
+        self.nx, self.ny, self.k0, self.k1, self.s, self.device = nx, ny, k0, k1, s, device
+        rc = self.L.greb_grid_create(C.byref(self.h), nx, ny, k0, k1, 2 * s, device)
+        if rc != 0:
+            msg = self.L.greb_grid_last_error(None).decode()
+            self.h = None
+            raise _lib.GrebError(f"greb_grid_create failed ({rc}): {msg}")
+        nsub, dt = C.c_int(), C.c_float()
+        self._ck(self.L.greb_grid_set_geometry(self.h, pi, kappa, C.byref(nsub), C.byref(dt)), "greb_grid_set_geometry")
+        self.nsub, self.dt_crcl = nsub.value, dt.value
+        self.kernel_ms = 0.0
+        self.launches = 0
+
+    def _ck(self, rc, what):
+        if rc != 0:
+            raise _lib.GrebError(f"{what} failed ({rc}): {self.L.greb_grid_last_error(self.h).decode()}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.greb_grid_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_fields(self, X, wz, u, v):
+        """FULL global host fields [ny][nx]; the band cuts out its rows and halos"""
+        arrs = [np.ascontiguousarray(a, dtype=np.float32) for a in (X, wz, u, v)]
+        assert all(a.shape == (self.ny, self.nx) for a in arrs)
+        self._ck(self.L.greb_grid_set_fields(self.h, *[_lib._p(a) for a in arrs]), "greb_grid_set_fields")
+
+    def substeps(self, n: int):
+        self._ck(self.L.greb_grid_substeps(self.h, n), "greb_grid_substeps")
+        ms, nl = C.c_float(), C.c_int()
+        self.L.greb_grid_last_ms(self.h, C.byref(ms), C.byref(nl))
+        self.kernel_ms += ms.value
+        self.launches += nl.value
+
+    def rows(self, lo: int, hi: int):
+        """torch view (no copy) of the global rows [lo, hi) of the current field buffer"""
+        import torch
+        ptr, kbase, nrows = C.c_void_p(), C.c_int(), C.c_int()
+        self._ck(self.L.greb_grid_view(self.h, C.byref(ptr), C.byref(kbase), C.byref(nrows), None, None), "greb_grid_view")
+        assert kbase.value <= lo <= hi <= kbase.value + nrows.value
+        addr = ptr.value + (lo - kbase.value) * self.nx * 4
+
+        class _A:
+            __cuda_array_interface__ = {"shape": (hi - lo, self.nx), "typestr": "<f4", "data": (addr, False), "version": 2}
+        return torch.as_tensor(_A(), device=f"cuda:{self.device}")
+
+    def halo_refreshed(self):
+        self._ck(self.L.greb_grid_halo_refreshed(self.h), "greb_grid_halo_refreshed")
+
+    def get(self) -> np.ndarray:
+        out = np.zeros((self.k1 - self.k0, self.nx), dtype=np.float32)
+        self._ck(self.L.greb_grid_get(self.h, _lib._p(out)), "greb_grid_get")
+        return out
+
+
+def exchange_halos(band, rank: int, world: int, group=None):
+    """Refresh the 2*s halo rows on both inner sides from the neighbours' own rows
+    (torch.distributed point-to-point: NCCL between GPUs, gloo in the CPU tests)."""
+    import torch.distributed as dist
+    h = 2 * band.s
+    ops, keep = [], []
+    if rank > 0:                                            # south neighbour
+        send = band.rows(band.k0, band.k0 + h)
+        recv = band.rows(band.k0 - h, band.k0)
+        ops += [dist.P2POp(dist.isend, send, rank - 1, group), dist.P2POp(dist.irecv, recv, rank - 1, group)]
+        keep += [send, recv]
+    if rank < world - 1:                                    # north neighbour
+        send = band.rows(band.k1 - h, band.k1)
+        recv = band.rows(band.k1, band.k1 + h)
+        ops += [dist.P2POp(dist.isend, send, rank + 1, group), dist.P2POp(dist.irecv, recv, rank + 1, group)]
+        keep += [send, recv]
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+        if keep[0].is_cuda:
+            # NCCL runs on torch's stream, the kernels on the handle's: the received rows must have
+            # landed before the next sub-step is launched
+            import torch
+            torch.cuda.current_stream(keep[0].device).synchronize()
+    band.halo_refreshed()
+
+
+def advance(band, n_substeps: int, rank: int = 0, world: int = 1, group=None) -> int:
+    """`n_substeps` circulation sub-steps of the whole domain, exchanging halos every band.s
+    sub-steps.  Returns the number of exchanges."""
+    if world > 1 and band.k1 - band.k0 < 2 * band.s:
+        raise ValueError(f"band of {band.k1 - band.k0} rows is thinner than the 2*s = {2 * band.s} halo rows")
+    done = exchanges = 0
+    while done < n_substeps:
+        n = min(band.s, n_substeps - done)
+        if world > 1:
+            exchange_halos(band, rank, world, group)
+            exchanges += 1
+        else:
+            band.halo_refreshed()
+        band.substeps(n)
+        done += n
+    return exchanges

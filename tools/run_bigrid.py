@@ -1,0 +1,170 @@
+#!/usr/bin/env python
+"""Config 5 of BASELINE.json: one member on a 0.25-degree (1440x720) grid, latitude bands over the
+GPUs of a node, halo rows exchanged between neighbours (NCCL point-to-point over NVLink).
+
+  python tools/run_bigrid.py --steps 1                                            # 1 GPU
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 \
+      --master-port 29512 tools/run_bigrid.py --steps 1 --period 16
+
+A 12-hour step here = the two circulations of the reference step (air temperature with wz_air,
+humidity with wz_vapor; src/greb.f90:299-304), each nint(43200/dt_crcl) = 5,400 sub-steps at
+0.25 degrees under the declared rules R1/R2 (include/greb_grid.h).  It is a strong-scaling
+experiment, not a parity target: the column physics needs no neighbour data and is
+not part of it.  Checks before timing: N-GPU result == 1-GPU result bit for bit after --verify
+sub-steps, and the first 4 sub-steps == oracle/grid_oracle.c (rank 0).  Rank 0 prints one JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "greb-climate-model_b200"))
+sys.path.insert(0, ROOT)
+
+
+def upsample(a: np.ndarray, ny: int, nx: int) -> np.ndarray:
+    """bilinear upsample of a [48][96] cell-centred field (periodic in longitude, clamped at the poles)"""
+    sy, sx = a.shape
+    y = (np.arange(ny) + 0.5) * sy / ny - 0.5
+    x = (np.arange(nx) + 0.5) * sx / nx - 0.5
+    y0 = np.clip(np.floor(y).astype(int), 0, sy - 1)
+    y1 = np.clip(y0 + 1, 0, sy - 1)
+    fy = np.clip(y - np.floor(y), 0, 1).astype(np.float32)
+    fy = np.where(np.floor(y) < 0, 0.0, fy).astype(np.float32)
+    x0 = np.floor(x).astype(int) % sx
+    x1 = (x0 + 1) % sx
+    fx = (x - np.floor(x)).astype(np.float32)
+    top = a[y0][:, x0] * (1 - fx) + a[y0][:, x1] * fx
+    bot = a[y1][:, x0] * (1 - fx) + a[y1][:, x1] * fx
+    return np.ascontiguousarray(top * (1 - fy[:, None]) + bot * fy[:, None], dtype=np.float32)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--nx", type=int, default=1440)
+    ap.add_argument("--ny", type=int, default=720)
+    ap.add_argument("--steps", type=float, default=1.0, help="12-hour steps to time (fractions allowed)")
+    ap.add_argument("--period", dest="s", type=int, default=16, help="sub-steps between halo exchanges (halo = 2*s rows)")
+    ap.add_argument("--verify", type=int, default=48, help="sub-steps of the N-GPU == 1-GPU check (0 = skip)")
+    args = ap.parse_args()
+
+    import torch
+    import torch.distributed as dist
+    from greb_b200 import bigrid, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("run_bigrid.py: no CUDA device — the B200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    nx, ny, s = args.nx, args.ny, args.s
+    f = synth.cached_forcing(cache_dir=os.environ.get("GREB_FORCING_CACHE", "/tmp/greb_b200_cache"))
+    ityr = 200
+    topo = upsample(f.z_topo, ny, nx)
+    fld = {"Ta": (upsample(f.tclim[ityr - 1], ny, nx), np.exp(-topo / np.float32(8400.0)).astype(np.float32)),
+           "q": (upsample(f.qclim[ityr - 1], ny, nx), np.exp(-topo / np.float32(5000.0)).astype(np.float32))}
+    u, v = upsample(f.uclim[ityr - 1], ny, nx), upsample(f.vclim[ityr - 1], ny, nx)
+    k0, k1 = bigrid.band_range(ny, world, rank)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def make(name, lo, hi):
+        b = bigrid.DeviceBand(nx, ny, lo, hi, s, device=local)
+        b.set_fields(fld[name][0], fld[name][1], u, v)
+        return b
+
+    checks = {}
+    # ---- correctness before timing -----------------------------------------------------------
+    if args.verify >= 4:
+        b = make("Ta", k0, k1)
+        bigrid.advance(b, args.verify, rank, world)
+        mine = torch.from_numpy(b.get()).to(f"cuda:{local}")
+        b.close()
+        if world > 1:                                          # gather the bands on every rank (padded: ragged heights)
+            sizes = [bigrid.band_range(ny, world, r) for r in range(world)]
+            pad = max(hi - lo for lo, hi in sizes)
+            buf = torch.zeros((pad, nx), dtype=torch.float32, device=f"cuda:{local}")
+            buf[:mine.shape[0]] = mine
+            allb = [torch.empty_like(buf) for _ in range(world)]
+            dist.all_gather(allb, buf)
+            full = torch.cat([allb[r][:hi - lo] for r, (lo, hi) in enumerate(sizes)]).cpu().numpy()
+        else:
+            full = mine.cpu().numpy()
+        if rank == 0:
+            one = make("Ta", 0, ny)
+            bigrid.advance(one, 4)
+            from oracle import grid as og                       # checker only
+            g = og.Geometry(nx, ny)
+            checks["first_4_substeps_equal_oracle"] = bool(np.array_equal(one.get(), og.substeps(g, fld["Ta"][0], fld["Ta"][1], u, v, 4)))
+            bigrid.advance(one, args.verify - 4)
+            checks[f"{world}_gpu_equals_1_gpu_after_{args.verify}_substeps"] = bool(np.array_equal(one.get(), full))
+            one.close()
+
+    # ---- timing ---------------------------------------------------------------------------------
+    bands = {n: make(n, k0, k1) for n in ("Ta", "q")}
+    nsub = bands["Ta"].nsub
+    n_time = max(s, int(round(args.steps * nsub)))
+    for b in bands.values():                                    # warm-up: 3 exchange periods
+        bigrid.advance(b, 3 * s, rank, world)
+        b.kernel_ms, b.launches = 0.0, 0
+    barrier()
+    t0 = time.perf_counter()
+    exchanges = 0
+    for b in bands.values():
+        exchanges += bigrid.advance(b, n_time, rank, world)
+    barrier()
+    wall = time.perf_counter() - t0
+    kms = sum(b.kernel_ms for b in bands.values())
+    launches = sum(b.launches for b in bands.values())
+    mean_T = float(bands["Ta"].get().astype(np.float64).mean())
+    t = torch.tensor([wall, kms], dtype=torch.float64, device=f"cuda:{local}")
+    m = torch.tensor([mean_T * (k1 - k0)], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(m)                                      # the global mean: the only collective
+    if rank == 0:
+        wall, kms = float(t[0]), float(t[1])
+        steps_done = n_time / nsub
+        line = {
+            "metric": "12-hour steps/s (circulations of one 0.25-degree member)", "value": steps_done / wall,
+            "unit": "steps/s", "n_gpus": world, "scaling": "strong",
+            "config": {"workload": "configs[4]: synthetic 1440x720 grid, single member, latitude bands, "
+                                   "S0 forcing bilinearly upsampled", "grid": f"{nx}x{ny}",
+                       "substeps_per_circulation": nsub, "dt_crcl_s": bands["Ta"].dt_crcl,
+                       "substeps_between_exchanges": s, "halo_rows": 2 * s,
+                       "rules": "R1 dt_crcl = 1800*(48/ydim)^2; R2 |lat| clamped to 88.125 deg in dxlat, dtdff2 >= 1 s",
+                       "exchange": "NCCL point-to-point of 2*s rows per neighbour every s sub-steps; "
+                                   "all-reduce of the global mean at the end"},
+            "timed_substeps_per_field": n_time, "wall_s": wall, "kernel_s_max_rank": kms / 1e3,
+            "cell_substeps_per_s": 2 * n_time * nx * ny / wall,
+            "gpu_launches_rank0": launches, "halo_exchanges_rank0": exchanges,
+            "halo_bytes_per_exchange_per_neighbour": 2 * s * nx * 4,
+            "global_mean_Ta": float(m[0]) / ny, "checks": checks,
+        }
+        print(json.dumps(line), flush=True)
+    for b in bands.values():
+        b.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

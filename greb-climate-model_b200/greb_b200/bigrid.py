@@ -23,7 +23,7 @@ from . import lib as _lib
 from . import sharding
 
 GRID_SYMBOLS = ["greb_grid_create", "greb_grid_destroy", "greb_grid_last_error", "greb_grid_set_geometry",
-                "greb_grid_set_fields", "greb_grid_substeps", "greb_grid_view", "greb_grid_halo_refreshed",
+                "greb_grid_set_fields", "greb_grid_substeps", "greb_grid_substeps_async", "greb_grid_sync", "greb_grid_view", "greb_grid_halo_refreshed",
                 "greb_grid_get", "greb_grid_last_ms"]
 _grid = None
 
@@ -48,6 +48,8 @@ def load_grid_library():
     L.greb_grid_set_geometry.argtypes = [vp, C.c_float, C.c_float, ip, fp]
     L.greb_grid_set_fields.argtypes = [vp, fp, fp, fp, fp]
     L.greb_grid_substeps.argtypes = [vp, C.c_int]
+    L.greb_grid_substeps_async.argtypes = [vp, C.c_int]
+    L.greb_grid_sync.argtypes = [vp]
     L.greb_grid_view.argtypes = [vp, C.POINTER(vp), ip, ip, ip, ip]
     L.greb_grid_halo_refreshed.argtypes = [vp]
     L.greb_grid_get.argtypes = [vp, fp]
@@ -107,6 +109,20 @@ class DeviceBand:
         self.L.greb_grid_last_ms(self.h, C.byref(ms), C.byref(nl))
         self.kernel_ms += ms.value
         self.launches += nl.value
+
+    def substeps_async(self, n: int):
+        """queue n sub-steps on the band's stream and return; `sync` waits for them"""
+        self._ck(self.L.greb_grid_substeps_async(self.h, n), "greb_grid_substeps_async")
+        self._pending = True
+
+    def sync(self):
+        self._ck(self.L.greb_grid_sync(self.h), "greb_grid_sync")
+        if getattr(self, "_pending", False):
+            ms, nl = C.c_float(), C.c_int()
+            self.L.greb_grid_last_ms(self.h, C.byref(ms), C.byref(nl))
+            self.kernel_ms += ms.value
+            self.launches += nl.value
+            self._pending = False
 
     def rows(self, lo: int, hi: int):
         """torch view (no copy) of the global rows [lo, hi) of the current field buffer"""
@@ -171,4 +187,29 @@ def advance(band, n_substeps: int, rank: int = 0, world: int = 1, group=None) ->
             band.halo_refreshed()
         band.substeps(n)
         done += n
+    return exchanges
+
+
+def advance_overlapped(bands, n_substeps: int, rank: int = 0, world: int = 1, group=None) -> int:
+    """The same for several independent fields of one band (air temperature and humidity of a step,
+    src/greb.f90:299-304) with the exchange of one field hidden behind the sub-steps of the others:
+    while field A's `s` sub-steps run on its stream, the host waits for field B's previous batch and
+    exchanges B's halos.  Returns the number of exchanges."""
+    s = bands[0].s
+    if world > 1 and any(b.k1 - b.k0 < 2 * b.s or b.s != s for b in bands):
+        raise ValueError("bands must share s and be at least 2*s rows high")
+    done = exchanges = 0
+    while done < n_substeps:
+        n = min(s, n_substeps - done)
+        for b in bands:
+            b.sync()                                        # its previous batch is complete
+            if world > 1:
+                exchange_halos(b, rank, world, group)
+                exchanges += 1
+            else:
+                b.halo_refreshed()
+            b.substeps_async(n)
+        done += n
+    for b in bands:
+        b.sync()
     return exchanges

@@ -38,6 +38,12 @@ int greb_grid_set_fields(greb_grid_t h, const float* X, const float* wz, const f
  * halo is too thin for n (exchange first). */
 int greb_grid_substeps(greb_grid_t h, int n);
 
+/* the same without waiting: the sub-steps are queued on the handle's stream, so the host can
+ * exchange another field's halos meanwhile; greb_grid_sync waits for them (and must be called
+ * before the band's rows are read or its halos rewritten) */
+int greb_grid_substeps_async(greb_grid_t h, int n);
+int greb_grid_sync(greb_grid_t h);
+
 /* device view for the halo exchange: pointer to local row 0 of the CURRENT field buffer, the
  * global index of that row, the number of local rows, and the global row range that is valid */
 int greb_grid_view(greb_grid_t h, float** dev_rows, int* kbase, int* nrows, int* valid_lo, int* valid_hi);

@@ -40,6 +40,12 @@ class OracleBand:
             self.cur ^= 1
             self.valid = (lo, hi)
 
+    def substeps_async(self, n):
+        self.substeps(n)
+
+    def sync(self):
+        pass
+
     def rows(self, lo, hi):
         import torch
         return torch.from_numpy(self.X[self.cur][lo - self.kbase:hi - self.kbase])

@@ -89,7 +89,12 @@ def _worker(rank, world, port, ret):
         b = OracleBand(nx, ny, k0, k1, s)
         b.set_fields(X, wz, u, v)
         ex = bigrid.advance(b, n, rank, world)
-        ret[rank] = (k0, k1, ex, b.get())
+        # two fields with overlapped exchanges (the second one circulates wz itself, like q with wz_vapor)
+        pair = [OracleBand(nx, ny, k0, k1, s), OracleBand(nx, ny, k0, k1, s)]
+        pair[0].set_fields(X, wz, u, v)
+        pair[1].set_fields(wz, wz, u, v)
+        ex2 = bigrid.advance_overlapped(pair, n, rank, world)
+        ret[rank] = (k0, k1, ex, b.get(), ex2, pair[0].get(), pair[1].get())
     finally:
         dist.destroy_process_group()
 
@@ -110,6 +115,10 @@ def test_advance_with_halo_exchange_gloo(world):
     assert [ret[r][:2] for r in range(world)] == [bigrid.band_range(ny, world, r) for r in range(world)]
     assert all(ret[r][2] == 4 for r in range(world))          # ceil(7 / 2) exchanges
     assert np.array_equal(got, want)
+    assert all(ret[r][4] == 8 for r in range(world))
+    assert np.array_equal(np.concatenate([ret[r][5] for r in range(world)]), want)
+    want2 = og.substeps(og.Geometry(nx, ny), wz, wz, u, v, n)
+    assert np.array_equal(np.concatenate([ret[r][6] for r in range(world)]), want2)
 
 
 def test_thin_band_is_refused():
@@ -207,3 +216,20 @@ def test_device_bands_with_halos_equal_the_undivided_domain():
 def greb_b200_error():
     import greb_b200
     return greb_b200.GrebError
+
+
+@pytest.mark.gpu
+def test_overlapped_fields_equal_sequential_runs():
+    nx, ny, s, n = 192, 96, 4, 11
+    X, wz, u, v = fields(nx, ny)
+    g = og.Geometry(nx, ny)
+    pair = [bigrid.DeviceBand(nx, ny, 0, ny, s), bigrid.DeviceBand(nx, ny, 0, ny, s)]
+    pair[0].set_fields(X, wz, u, v)
+    pair[1].set_fields(wz, wz, u, v)
+    assert bigrid.advance_overlapped(pair, n) == 0
+    got = [b.get() for b in pair]
+    assert pair[0].launches == n and pair[0].kernel_ms > 0
+    for b in pair:
+        b.close()
+    assert np.array_equal(got[0], og.substeps(g, X, wz, u, v, n))
+    assert np.array_equal(got[1], og.substeps(g, wz, wz, u, v, n))

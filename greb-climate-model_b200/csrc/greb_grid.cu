@@ -6,7 +6,7 @@
 // sub-sub-steps (f:655-718, f:841-910) ping-pong between two shared buffers, the y-direction terms
 // read rows k-2..k+2 of the previous sub-step from global memory (L2-resident: a 1440x720 field is
 // 4 MB).  Expressions keep the reference's operand order; the file is compiled with -fmad=false and
-// IEEE division, so results are bit-identical to oracle/grid_oracle.c (and at 96x48 to the
+// IEEE division, so results are bit-identical to the CPU restatement the tests check against (and at 96x48 to the
 // reference arithmetic).  No CPU path.
 #include <cuda_runtime.h>
 #include <math.h>

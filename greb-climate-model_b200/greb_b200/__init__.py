@@ -5,9 +5,9 @@ package is the thin ctypes layer over it plus the reference's host-side formats 
 input/output files) and the synthetic forcing generator.  There is no CPU implementation here:
 everything numerical goes through the C ABI and needs a B200.
 """
-from . import campaign, host, sharding, synth  # noqa: F401
+from . import bigrid, campaign, host, sharding, synth  # noqa: F401
 from .lib import (Ensemble, GrebError, Physics, build_library, default_physics, library_path,  # noqa: F401
                   load_library, original_physics, pad_co2)
 
 __all__ = ["Ensemble", "GrebError", "Physics", "build_library", "default_physics", "original_physics",
-           "library_path", "load_library", "pad_co2", "synth", "host", "sharding", "campaign"]
+           "library_path", "load_library", "pad_co2", "synth", "host", "sharding", "campaign", "bigrid"]

@@ -11,7 +11,7 @@
  * The reference formulas cannot run at 0.25 degrees as written.  Declared rules,
  * both inactive on the reference's 96x48 grid (there the results are bit-identical to the
  * reference arithmetic):  R1  dt_crcl = 1800*(48/ydim)^2 s;  R2  the latitude entering dxlat is
- * clamped to +-88.125 degrees and dtdff2 is floored at 1 s.  (oracle/grid_oracle.c restates them.)
+ * clamped to +-88.125 degrees and dtdff2 is floored at 1 s.  (The test suite carries a CPU restatement of both.)
  *
  * All functions return 0 or a negative error code; greb_grid_last_error gives the message.
  * No CPU fallback: greb_grid_create fails without an sm_100 device. */

@@ -36,14 +36,27 @@ __device__ __forceinline__ void pad_fix(float* p, int nx) {  // p points at elem
   else if (t < 6) p[nx + t - 3] = p[t - 3];
 }
 
+// Correctly rounded x/3 and x/20 without the division subroutine: q0 = x*RN(1/d); r = fma(-d,q0,x);
+// q = fma(r,RN(1/d),q0) equals RN(x/d) for every float x whose quotient is a normal number (the same
+// sequences as greb_core.h, verified exhaustively over all 2^32 inputs: tests/test_divc.py).
+__device__ __forceinline__ float div3(float x) {
+  const float r = 0.3333333432674407958984375f;
+  const float q = __fmul_rn(x, r);
+  return __fmaf_rn(__fmaf_rn(-3.0f, q, x), r, q);
+}
+__device__ __forceinline__ float div20(float x) {
+  const float r = 0.0500000007450580596923828125f;
+  const float q = __fmul_rn(x, r);
+  return __fmaf_rn(__fmaf_rn(-20.0f, q, x), r, q);
+}
+
 // f:595-650 / f:659-714 at longitude j of padded rows
 __device__ __forceinline__ float diff_x(const float* T, const float* w, int j, float cc) {
-  return cc * (10.f * (w[j - 1] * (T[j - 1] - T[j]) + w[j + 1] * (T[j + 1] - T[j])) +
+  return div20(cc * (10.f * (w[j - 1] * (T[j - 1] - T[j]) + w[j + 1] * (T[j + 1] - T[j])) +
                4.f * (w[j - 2] * (T[j - 2] - T[j - 1]) + w[j - 1] * (T[j] - T[j - 1])) +
                4.f * (w[j + 1] * (T[j] - T[j + 1]) + w[j + 2] * (T[j + 2] - T[j + 1])) +
                1.f * (w[j - 3] * (T[j - 3] - T[j - 2]) + w[j - 2] * (T[j - 1] - T[j - 2])) +
-               1.f * (w[j + 2] * (T[j + 1] - T[j + 2]) + w[j + 3] * (T[j + 3] - T[j + 2]))) /
-         20.f;
+               1.f * (w[j + 2] * (T[j + 1] - T[j + 2]) + w[j + 3] * (T[j + 3] - T[j + 2]))));
 }
 
 __global__ void __launch_bounds__(GG_THREADS) greb_grid_substep_kernel(const GridArgs a) {
@@ -54,10 +67,17 @@ __global__ void __launch_bounds__(GG_THREADS) greb_grid_substep_kernel(const Gri
   float* wp = sm + stride + 3;      // wz of the row (padded)
   float* A = sm + 2 * stride + 3;   // ping-pong buffers of the polar sub-sub-steps
   float* B = sm + 3 * stride + 3;
-#define G(p, kk, jj) ((p)[(size_t)(kk) * nx + (jj)])
+  // row base pointers (rows outside the domain are never dereferenced)
+  const float* Xk = a.X + (size_t)k * nx;
+  const float *Xm1 = Xk - nx, *Xm2 = Xk - 2 * nx, *Xp1 = Xk + nx, *Xp2 = Xk + 2 * nx;
+  const float* Wk = a.wz + (size_t)k * nx;
+  const float *Wm1 = Wk - nx, *Wm2 = Wk - 2 * nx, *Wp1 = Wk + nx, *Wp2 = Wk + 2 * nx;
+  const float* Uk = a.u + (size_t)k * nx;
+  const float* Vk = a.v + (size_t)k * nx;
+  float* Ok = a.Xnew + (size_t)k * nx;
   for (int j = tid; j < nx; j += GG_THREADS) {
-    T0[j] = G(a.X, k, j);
-    wp[j] = G(a.wz, k, j);
+    T0[j] = Xk[j];
+    wp[j] = Wk[j];
   }
   __syncthreads();
   pad_fix(T0, nx);
@@ -76,29 +96,29 @@ __global__ void __launch_bounds__(GG_THREADS) greb_grid_substep_kernel(const Gri
       // ---- y part of the diffusion, f:587-590
       float dTy;
       if (k >= 1 && k <= ny - 2)
-        dTy = a.ccy_d * (G(a.wz, k - 1, j) * (G(a.X, k - 1, j) - T) + G(a.wz, k + 1, j) * (G(a.X, k + 1, j) - T));
+        dTy = a.ccy_d * (Wm1[j] * (Xm1[j] - T) + Wp1[j] * (Xp1[j] - T));
       else if (k == 0)
-        dTy = a.ccy_d * G(a.wz, k + 1, j) * (-T + G(a.X, k + 1, j));
+        dTy = a.ccy_d * Wp1[j] * (-T + Xp1[j]);
       else
-        dTy = a.ccy_d * G(a.wz, k - 1, j) * (G(a.X, k - 1, j) - T);
+        dTy = a.ccy_d * Wm1[j] * (Xm1[j] - T);
       dd[c] = dTy;
       // ---- y part of the advection, f:756-795 (five row cases, different parenthesisation)
-      const float vv = G(a.v, k, j);
+      const float vv = Vk[j];
       const float vm = vv >= 0.f ? vv : 0.f, vp = vv >= 0.f ? 0.f : vv;  // f:205-214
       float aTy;
       if (k == 0)
-        aTy = a.ccy_a * (vp * (G(a.wz, k + 1, j) * (T - G(a.X, k + 1, j)) + G(a.wz, k + 2, j) * (T - G(a.X, k + 2, j)))) / 3.f;
+        aTy = div3(a.ccy_a * (vp * (Wp1[j] * (T - Xp1[j]) + Wp2[j] * (T - Xp2[j]))));
       else if (k == 1)
-        aTy = a.ccy_a * (-vm * (G(a.wz, k - 1, j) * (T - G(a.X, k - 1, j))) +
-                         vp * (G(a.wz, k + 1, j) * (T - G(a.X, k + 1, j)) + G(a.wz, k + 2, j) * (T - G(a.X, k + 2, j))) / 3.f);
+        aTy = a.ccy_a * (-vm * (Wm1[j] * (T - Xm1[j])) +
+                         div3(vp * (Wp1[j] * (T - Xp1[j]) + Wp2[j] * (T - Xp2[j]))));
       else if (k <= ny - 3)
-        aTy = a.ccy_a * (-vm * (G(a.wz, k - 1, j) * (T - G(a.X, k - 1, j)) + G(a.wz, k - 2, j) * (T - G(a.X, k - 2, j))) +
-                         vp * (G(a.wz, k + 1, j) * (T - G(a.X, k + 1, j)) + G(a.wz, k + 2, j) * (T - G(a.X, k + 2, j)))) / 3.f;
+        aTy = div3(a.ccy_a * (-vm * (Wm1[j] * (T - Xm1[j]) + Wm2[j] * (T - Xm2[j])) +
+                              vp * (Wp1[j] * (T - Xp1[j]) + Wp2[j] * (T - Xp2[j]))));
       else if (k == ny - 2)
-        aTy = a.ccy_a * (-vm * (G(a.wz, k - 1, j) * (T - G(a.X, k - 1, j)) + G(a.wz, k - 2, j) * (T - G(a.X, k - 2, j))) / 3.f +
-                         vp * (G(a.wz, k + 1, j) * (T - G(a.X, k + 1, j))));
+        aTy = a.ccy_a * (div3(-vm * (Wm1[j] * (T - Xm1[j]) + Wm2[j] * (T - Xm2[j]))) +
+                         vp * (Wp1[j] * (T - Xp1[j])));
       else
-        aTy = a.ccy_a * (-vm * (G(a.wz, k - 1, j) * (T - G(a.X, k - 1, j)) + G(a.wz, k - 2, j) * (T - G(a.X, k - 2, j)))) / 3.f;
+        aTy = div3(a.ccy_a * (-vm * (Wm1[j] * (T - Xm1[j]) + Wm2[j] * (T - Xm2[j]))));
       adv[c] = aTy;
     }
   }
@@ -109,7 +129,7 @@ __global__ void __launch_bounds__(GG_THREADS) greb_grid_substep_kernel(const Gri
 #pragma unroll
     for (int c = 0; c < GG_MAXC; ++c) {
       const int j = tid + c * GG_THREADS;
-      if (j < nx) dd[c] = G(a.wz, k, j) * (diff_x(T0, wp, j, cc) + dd[c]);  // f:721
+      if (j < nx) dd[c] = wp[j] * (diff_x(T0, wp, j, cc) + dd[c]);  // f:721
     }
   } else {  // f:651-718
     const int time2 = a.t2d[k];
@@ -131,7 +151,7 @@ __global__ void __launch_bounds__(GG_THREADS) greb_grid_substep_kernel(const Gri
 #pragma unroll
     for (int c = 0; c < GG_MAXC; ++c) {
       const int j = tid + c * GG_THREADS;
-      if (j < nx) dd[c] = G(a.wz, k, j) * ((cur[j] - T0[j]) + dd[c]);  // f:718, f:721
+      if (j < nx) dd[c] = wp[j] * ((cur[j] - T0[j]) + dd[c]);  // f:718, f:721
     }
     __syncthreads();  // A/B are reused below
   }
@@ -143,10 +163,10 @@ __global__ void __launch_bounds__(GG_THREADS) greb_grid_substep_kernel(const Gri
     for (int c = 0; c < GG_MAXC; ++c) {
       const int j = tid + c * GG_THREADS;
       if (j < nx) {
-        const float uu = G(a.u, k, j);
+        const float uu = Uk[j];
         const float um = uu >= 0.f ? uu : 0.f, up = uu >= 0.f ? 0.f : uu;
-        const float dTx = cc * (-um * (wp[j - 1] * (T0[j] - T0[j - 1]) + wp[j - 2] * (T0[j] - T0[j - 2])) +
-                                up * (wp[j + 1] * (T0[j] - T0[j + 1]) + wp[j + 2] * (T0[j] - T0[j + 2]))) / 3.f;
+        const float dTx = div3(cc * (-um * (wp[j - 1] * (T0[j] - T0[j - 1]) + wp[j - 2] * (T0[j] - T0[j - 2])) +
+                                     up * (wp[j + 1] * (T0[j] - T0[j + 1]) + wp[j + 2] * (T0[j] - T0[j + 2]))));
         adv[c] = dTx + adv[c];  // f:913
       }
     }
@@ -157,7 +177,7 @@ __global__ void __launch_bounds__(GG_THREADS) greb_grid_substep_kernel(const Gri
     float* nxt = A;
     for (int tt = 0; tt < time2; ++tt) {
       for (int j = tid; j < nx; j += GG_THREADS) {
-        const float uu = G(a.u, k, j);
+        const float uu = Uk[j];
         const float um = uu >= 0.f ? uu : 0.f, up = uu >= 0.f ? 0.f : uu;
         int jp1 = j + 1, jp2 = j + 2, jp3 = j + 3;
         if (j == nx - 3) {  // f:880-888: the reference sets jp2 = xdim-1 here (should be xdim)
@@ -165,10 +185,10 @@ __global__ void __launch_bounds__(GG_THREADS) greb_grid_substep_kernel(const Gri
           jp2 = nx - 2;
           jp3 = 0;
         }
-        float d = cc * (-um * (10.f * wp[j - 1] * (cur[j] - cur[j - 1]) + 4.f * wp[j - 2] * (cur[j - 1] - cur[j - 2]) +
-                               1.f * wp[j - 3] * (cur[j - 2] - cur[j - 3])) +
-                        up * (10.f * wp[jp1] * (cur[j] - cur[jp1]) + 4.f * wp[jp2] * (cur[jp1] - cur[jp2]) +
-                              1.f * wp[jp3] * (cur[jp2] - cur[jp3]))) / 20.f;
+        float d = div20(cc * (-um * (10.f * wp[j - 1] * (cur[j] - cur[j - 1]) + 4.f * wp[j - 2] * (cur[j - 1] - cur[j - 2]) +
+                                     1.f * wp[j - 3] * (cur[j - 2] - cur[j - 3])) +
+                              up * (10.f * wp[jp1] * (cur[j] - cur[jp1]) + 4.f * wp[jp2] * (cur[jp1] - cur[jp2]) +
+                                    1.f * wp[jp3] * (cur[jp2] - cur[jp3]))));
         if (d <= -cur[j]) d = -0.9f * cur[j];  // f:907
         nxt[j] = cur[j] + d;                   // f:908
       }
@@ -188,9 +208,8 @@ __global__ void __launch_bounds__(GG_THREADS) greb_grid_substep_kernel(const Gri
 #pragma unroll
   for (int c = 0; c < GG_MAXC; ++c) {
     const int j = tid + c * GG_THREADS;
-    if (j < nx) G(a.Xnew, k, j) = T0[j] + dd[c] + adv[c];  // f:549
+    if (j < nx) Ok[j] = T0[j] + dd[c] + adv[c];  // f:549
   }
-#undef G
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -41,6 +41,21 @@ def perturbed_member(g: int):
     return p, co2
 
 
+# device bytes of one perturbed member: its own flux corrections (src/greb.f90:110, 3 x 730 fields), state,
+# accumulators and the double-buffered year of monthly means
+BYTES_PER_MEMBER = (3 * 730 + 5 + 6 + 2 * 12 * 5) * 96 * 48 * 4
+SHARED_BYTES = 730 * 10 * 96 * 48 * 4          # forcing + spin-up targets, once per handle
+
+
+def auto_batch(free_bytes: int, reserve: int = 4 << 30, multiple: int = 148) -> int:
+    """largest batch (a multiple of the SM count: whole waves of one CTA per SM) whose device arrays
+    fit into `free_bytes` with `reserve` left over; at least one member"""
+    n = (int(free_bytes) - reserve - SHARED_BYTES) // BYTES_PER_MEMBER
+    if n >= multiple:
+        n -= n % multiple
+    return max(1, int(n))
+
+
 def plan_batches(n_local: int, batch: int) -> List[Tuple[int, int]]:
     """[start, stop) slices of a rank's members, sizes as equal as possible and <= batch."""
     if n_local < 0 or batch < 1:
@@ -53,7 +68,7 @@ def plan_batches(n_local: int, batch: int) -> List[Tuple[int, int]]:
 
 def run_sharded(total_members: int, member_fn: Callable[[int], Tuple["_lib.Physics", Sequence[float]]], forcing,
                 time_flux: int, time_scnr: int, *, rank: int = 0, world: int = 1, device: int = 0,
-                batch: int = 2048, arith: str = "exact", out_stride: int = 1024, year0: int = 1940,
+                batch: int | None = 2048, arith: str = "exact", out_stride: int = 1024, year0: int = 1940,
                 ensemble_cls=None, reduce: bool = True) -> Dict:
     """Run members [0, total_members) of an ensemble, this process doing rank `rank`'s share.
 
@@ -70,6 +85,9 @@ def run_sharded(total_members: int, member_fn: Callable[[int], Tuple["_lib.Physi
     ms_spin = ms_scen = 0.0
     launches = 0
     t_setup = t_spin = t_scen = 0.0
+    if not batch:                                       # size the batches from the free device memory
+        import torch
+        batch = auto_batch(torch.cuda.mem_get_info(device)[0])
     batches = plan_batches(n_local, batch)
     for b0, b1 in batches:
         nb = b1 - b0

@@ -27,6 +27,17 @@ def test_plan_batches_covers_the_shard():
         campaign.plan_batches(4, 0)
 
 
+def test_auto_batch_fits_the_device():
+    per = campaign.BYTES_PER_MEMBER
+    assert 40.0e6 < per < 43.5e6                                   # 40.4 MB of corrections + state + outputs
+    b = campaign.auto_batch(180 << 30)
+    assert b % 148 == 0 and 3800 <= b <= 4400                     # "about 4,000 perturbed members fit one B200"
+    assert b * per + campaign.SHARED_BYTES + (4 << 30) <= (180 << 30)
+    assert campaign.auto_batch(1 << 30) == 1                      # never zero: init reports the shortage itself
+    small = campaign.auto_batch(5 << 30)                          # less than one wave fits: no rounding down to 0
+    assert 1 <= small < 148
+
+
 def test_perturbed_member_draws_are_reproducible_and_in_range():
     p0, c0 = campaign.perturbed_member(0)
     p1, c1 = campaign.perturbed_member(0)

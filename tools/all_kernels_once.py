@@ -48,4 +48,4 @@ for world in (1, 3):
         b.substeps(s)
         b.get()
         b.close()
-print("sanitize_small: done")
+print("all_kernels_once: done")

@@ -712,7 +712,7 @@ GDEV void circulation_main(const SimtCtx& ctx, Tile& t, const RowGeom& g, const 
   if (g.owned) tile_publish(t, g, ss.hb + (ss.phase & 1) * GNC);
   sb_arrive(ctx, ss.bar);
 #if defined(GREB_DBG_CLOCKS) && GREB_DEVICE
-  // timing experiment (tools/debug_circ.py): cycles per sub-step in the x part, the barrier and the y part
+  // timing experiment (tests/debug/debug_circ.py): cycles per sub-step in the x part, the barrier and the y part
   long long c_x = 0, c_w = 0, c_y = 0;
 #define GCLK(acc, t0) { const long long t1_ = clock64(); acc += t1_ - t0; t0 = t1_; }
   long long tc = clock64();

@@ -2,7 +2,7 @@
 """Debug helper: one circulation call on the GPU against the oracle; prints the differing cells."""
 import os, sys
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(ROOT, "greb-climate-model_b200")); sys.path.insert(0, ROOT)
 import greb_b200
 from greb_b200 import synth

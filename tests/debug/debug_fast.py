@@ -2,7 +2,7 @@
 """Fast arithmetic mode against the oracle: circulation differences, 5-year drift, speed."""
 import os, sys, time
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(ROOT, "greb-climate-model_b200")); sys.path.insert(0, ROOT)
 import greb_b200
 from greb_b200 import synth

@@ -141,7 +141,8 @@ def test_grid_library_exports_the_abi():
 
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.gpu
-@pytest.mark.parametrize("nx,ny,n", [(96, 48, 24), (192, 96, 10), (1440, 64, 3), (1536, 24, 2), (40, 720, 2)])
+@pytest.mark.parametrize("nx,ny,n", [(96, 48, 24), (192, 96, 10), (1440, 64, 3), (1536, 24, 2), (40, 720, 2),
+                                     (1440, 720, 4)])
 def test_device_band_is_bit_exact(nx, ny, n):
     X, wz, u, v = fields(nx, ny, seed=nx + ny)
     g = og.Geometry(nx, ny)

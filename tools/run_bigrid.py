@@ -10,8 +10,9 @@ A 12-hour step here = the two circulations of the reference step (air temperatur
 humidity with wz_vapor; src/greb.f90:299-304), each nint(43200/dt_crcl) = 5,400 sub-steps at
 0.25 degrees under the declared rules R1/R2 (include/greb_grid.h).  It is a strong-scaling
 experiment, not a parity target: the column physics needs no neighbour data and is
-not part of it.  Checks before timing: N-GPU result == 1-GPU result bit for bit after --verify
-sub-steps, and the first 4 sub-steps == oracle/grid_oracle.c (rank 0).  Rank 0 prints one JSON line.
+not part of it.  Check before timing: N-GPU result == 1-GPU result bit for bit after --verify
+sub-steps (parity with the CPU restatement, also at 1440x720, is tests/test_grid_path.py's job).
+Rank 0 prints one JSON line.
 """
 from __future__ import annotations
 
@@ -25,7 +26,6 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "greb-climate-model_b200"))
-sys.path.insert(0, ROOT)
 
 
 def upsample(a: np.ndarray, ny: int, nx: int) -> np.ndarray:
@@ -93,7 +93,7 @@ def main():
 
     checks = {}
     # ---- correctness before timing -----------------------------------------------------------
-    if args.verify >= 4:
+    if args.verify > 0:
         b = make("Ta", k0, k1)
         bigrid.advance(b, args.verify, rank, world)
         mine = torch.from_numpy(b.get()).to(f"cuda:{local}")
@@ -110,11 +110,7 @@ def main():
             full = mine.cpu().numpy()
         if rank == 0:
             one = make("Ta", 0, ny)
-            bigrid.advance(one, 4)
-            from oracle import grid as og                       # checker only
-            g = og.Geometry(nx, ny)
-            checks["first_4_substeps_equal_oracle"] = bool(np.array_equal(one.get(), og.substeps(g, fld["Ta"][0], fld["Ta"][1], u, v, 4)))
-            bigrid.advance(one, args.verify - 4)
+            bigrid.advance(one, args.verify)
             checks[f"{world}_gpu_equals_1_gpu_after_{args.verify}_substeps"] = bool(np.array_equal(one.get(), full))
             one.close()
 

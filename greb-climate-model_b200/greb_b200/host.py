@@ -466,3 +466,51 @@ def run_original_namelist(namelist: str = "namelist_original", input_dir: str = 
         write_control(os.path.join(workdir, "output", "control"), r["tf_correct"], r["control"])
         write_output(os.path.join(workdir, "output", "scenario"), r["scenario"])
     return r
+
+
+# ------------------------------------------------------------------------------------------------
+# spin-up cache on disk: qflux_correction (f:311-364) once per (inputs, physics, years)
+# ------------------------------------------------------------------------------------------------
+def spinup_key(forcing: "synth.Forcing", physics: "_lib.Physics", time_flux: int, switches: int = 0,
+               arith: str = "exact") -> str:
+    """Everything the flux-correction spin-up depends on: the ten input fields, physics_par incl.
+    co2_flux (the spin-up CO2, f:221), the spin-up-relevant process switches, its length, and the
+    arithmetic mode (exact and fast corrections differ in the last bits)."""
+    import ctypes
+    import hashlib
+    h = hashlib.sha256()
+    h.update(forcing.digest().encode())
+    h.update(ctypes.string_at(ctypes.byref(physics), ctypes.sizeof(physics)))
+    h.update(f"|{int(time_flux)}|{int(switches) & ~_lib.SW_SST_PLUS_1K}|{arith}".encode())
+    return h.hexdigest()[:32]
+
+
+def save_spinup(path: str, ens: "_lib.Ensemble", member: int, key: str) -> None:
+    """Write member `member`'s post-spin-up state (Ts, Ta, To, q, cap_surf) and the three flux
+    correction fields of its physics group (TF, qF, ToF; 40.4 MB) to `path` (.npz)."""
+    d = {"key": np.array(key), "state": np.stack([ens.get_state(member, n) for n in _lib.STATE])}
+    for w, name in enumerate(("tf_correct", "qf_correct", "tof_correct")):
+        d[name] = ens.get_fluxcorr(member, w)
+    os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+    tmp = path + ".tmp.npz"
+    np.savez(tmp, **d)
+    os.replace(tmp, path)
+
+
+def load_spinup(path: str, ens: "_lib.Ensemble", members: Sequence[int], key: str) -> bool:
+    """Restore a saved spin-up into `members` (all of one physics group: the corrections are set
+    through the first of them) of an initialised handle instead of calling `spinup`.  Returns False
+    — and touches nothing — if the file is missing or was written for another key."""
+    if not os.path.exists(path):
+        return False
+    with np.load(path) as z:
+        if str(z["key"]) != key:
+            return False
+        state = z["state"]
+        corr = [z[n] for n in ("tf_correct", "qf_correct", "tof_correct")]
+    for w, a in enumerate(corr):
+        ens.set_fluxcorr(members[0], w, a)
+    for m in members:
+        for i, n in enumerate(_lib.STATE):
+            ens.set_state(m, n, state[i])
+    return True

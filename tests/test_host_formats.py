@@ -111,3 +111,36 @@ def test_output_stream_and_read_greb_roundtrip(tmp_path):
 def test_read_inputs_reports_missing_files(tmp_path):
     with pytest.raises(FileNotFoundError):
         host.read_inputs(str(tmp_path))
+
+
+class _CacheEns:
+    """host-memory stand-in with the accessor names of greb_b200.Ensemble (the disk format is what is tested)"""
+
+    def __init__(self, seed):
+        rng = np.random.default_rng(seed)
+        self.state = {n: rng.normal(280, 5, (48, 96)).astype(np.float32) for n in lib.STATE}
+        self.corr = [rng.normal(0, 30, (730, 48, 96)).astype(np.float32) for _ in range(3)]
+
+    def get_state(self, m, n): return self.state[n]
+    def get_fluxcorr(self, m, w): return self.corr[w]
+    def set_state(self, m, n, a): self.state[n] = np.array(a, copy=True)
+    def set_fluxcorr(self, m, w, a): self.corr[w] = np.array(a, copy=True)
+
+
+def test_spinup_cache_roundtrip_and_key(forcing, tmp_path):
+    p = lib.default_physics()
+    k1 = host.spinup_key(forcing, p, 3)
+    assert k1 == host.spinup_key(forcing, p, 3, switches=lib.SW_SST_PLUS_1K)   # scenario-only switch
+    p2 = lib.default_physics()
+    p2.kappa = 9e5
+    keys = {k1, host.spinup_key(forcing, p2, 3), host.spinup_key(forcing, p, 2),
+            host.spinup_key(forcing, p, 3, switches=lib.SW_NO_HYDRO), host.spinup_key(forcing, p, 3, arith="fast")}
+    assert len(keys) == 5
+    a, b = _CacheEns(1), _CacheEns(2)
+    path = str(tmp_path / "cache" / f"spinup_{k1}.npz")
+    assert not host.load_spinup(path, b, [0], k1)                      # nothing there yet
+    host.save_spinup(path, a, 0, k1)
+    assert not host.load_spinup(path, b, [0], "another key") and not np.array_equal(b.corr[0], a.corr[0])
+    assert host.load_spinup(path, b, [0, 1], k1)
+    assert all(np.array_equal(a.corr[w], b.corr[w]) for w in range(3))
+    assert all(np.array_equal(a.state[n], b.state[n]) for n in a.state)

@@ -335,3 +335,25 @@ def test_spinup_cache_restores_a_run_bit_for_bit(forcing):
     out2, gm2, _ = e2.run(2)
     assert np.array_equal(out1, out2) and np.array_equal(gm1, gm2)
     e2.close()
+
+
+@pytest.mark.gpu
+def test_spinup_cache_on_disk(forcing, tmp_path):
+    """host.save_spinup / load_spinup: a second handle restored from the file continues bit for bit"""
+    from greb_b200 import host
+    p = product_physics(kappa=8.6e5)
+    key = host.spinup_key(forcing, p, 1)
+    path = str(tmp_path / f"spinup_{key}.npz")
+    e1 = make_ensemble(forcing, [p], [[500.0]])
+    e1.spinup(1)
+    host.save_spinup(path, e1, 0, key)
+    e1.reset_scenario()
+    out1, gm1, _ = e1.run(1)
+    e1.close()
+    e2 = make_ensemble(forcing, [p, p], [[500.0], [500.0]])   # two members of one physics group
+    assert not host.load_spinup(path, e2, [0, 1], host.spinup_key(forcing, p, 2))
+    assert host.load_spinup(path, e2, [0, 1], key)
+    e2.reset_scenario()
+    out2, gm2, _ = e2.run(1)
+    e2.close()
+    assert np.array_equal(out2[0], out1[0]) and np.array_equal(out2[1], out1[0]) and gm2[1, 0] == gm1[0, 0]

@@ -139,6 +139,15 @@ struct greb_b200_handle_s {
   int last_out = 0;  // d_out buffer holding the last completed year
   float last_ms = 0.f;
   int last_launches = 0;
+  // asynchronous run (greb_b200_run_async / greb_b200_wait)
+  long long year_seq = 0;              // years launched since greb_b200_init: d_out slot = year_seq & 1
+  bool copy_pending[2] = {false, false};  // ev_c[b] recorded and not yet known to be complete
+  bool pending = false;                // a run_async has not been waited for
+  int pend_years = 0;
+  float *pend_gmean = nullptr, *pend_gcos = nullptr;
+  float* d_diag_hist = nullptr;        // [hist_years][n_members][2] annual diagnostics of the pending call
+  float* h_diag_hist = nullptr;        // pinned mirror
+  int hist_years = 0;
 };
 
 static std::string g_create_err;
@@ -150,6 +159,14 @@ static std::string g_create_err;
       h->err = std::string(#call) + ": " + cudaGetErrorString(e_);                                \
       return GREB_E_CUDA;                                                                         \
     }                                                                                             \
+  } while (0)
+
+static int finish_pending(greb_b200_t h);
+// completes an asynchronous run before an entry point touches device state or the calendar
+#define FIN(h)                                  \
+  do {                                          \
+    const int rc_ = finish_pending(h);          \
+    if (rc_ != GREB_OK) return rc_;             \
   } while (0)
 
 static int fail(greb_b200_t h, int code, const std::string& msg) {
@@ -227,11 +244,19 @@ static void free_device(greb_b200_t h) {
   }
   if (h->d_mc) cudaFree(h->d_mc);
   h->d_mc = nullptr;
+  if (h->d_diag_hist) cudaFree(h->d_diag_hist);
+  h->d_diag_hist = nullptr;
+  if (h->h_diag_hist) cudaFreeHost(h->h_diag_hist);
+  h->h_diag_hist = nullptr;
+  h->hist_years = 0;
+  h->pending = false;
+  h->copy_pending[0] = h->copy_pending[1] = false;
 }
 
 extern "C" int greb_b200_destroy(greb_b200_t h) {
   if (!h) return GREB_E_INVALID;
   cudaSetDevice(h->device);
+  finish_pending(h);
   cudaDeviceSynchronize();
   free_device(h);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -302,8 +327,9 @@ extern "C" int greb_b200_set_switches(greb_b200_t h, int member, unsigned mask) 
     if (spinup_switches(mask) != spinup_switches(h->switches[member]))
       return fail(h, GREB_E_INVALID,
                   "greb_b200_set_switches: after greb_b200_init only GREB_SW_SST_PLUS_1K may be toggled");
-    h->switches[member] = mask;
     cudaSetDevice(h->device);
+    FIN(h);
+    h->switches[member] = mask;
     const int sw = (int)mask;
     CK(cudaMemcpyAsync(reinterpret_cast<char*>(h->d_mc + member) + offsetof(GrebMemberConst, switches), &sw,
                        sizeof(int), cudaMemcpyHostToDevice, h->stream));
@@ -325,6 +351,10 @@ extern "C" int greb_b200_init(greb_b200_t h) {
   if (!h) return GREB_E_INVALID;
   if (!h->have_forcing) return fail(h, GREB_E_INVALID, "greb_b200_init: set_forcing has not been called");
   cudaSetDevice(h->device);
+  finish_pending(h);
+  h->inited = false;  // stays false if anything below fails: no entry point may touch half-built device state
+  cudaStreamSynchronize(h->stream);
+  cudaStreamSynchronize(h->copy_stream);
   free_device(h);
   const int N = h->n_members;
   // physics groups: members with identical physics_par share wz fields, spin-up and corrections
@@ -417,6 +447,7 @@ extern "C" int greb_b200_init(greb_b200_t h) {
   CK(cudaMalloc((void**)&h->d_flags, (size_t)N * 4));
   CK(cudaMemset(h->d_flags, 0, (size_t)N * 4));
   h->it_next = 1;
+  h->year_seq = 0;
   h->inited = true;
   return GREB_OK;
 }
@@ -452,6 +483,7 @@ extern "C" int greb_b200_spinup(greb_b200_t h, int years) {
   if (!h->inited) return fail(h, GREB_E_INVALID, "greb_b200_spinup: greb_b200_init has not been called");
   if (years < 0) return fail(h, GREB_E_INVALID, "greb_b200_spinup: years < 0");
   cudaSetDevice(h->device);
+  FIN(h);
   const int G = (int)h->group_rep.size();
   GrebKernelArgs a = base_args(h);
   a.member_ids = h->d_ids_rep;
@@ -482,6 +514,7 @@ extern "C" int greb_b200_reset_scenario(greb_b200_t h) {
   if (!h) return GREB_E_INVALID;
   if (!h->inited) return fail(h, GREB_E_INVALID, "greb_b200_reset_scenario: not initialised");
   cudaSetDevice(h->device);
+  FIN(h);
   // f:227: year=year0, mon=1, irec=0, monthly accumulators zero (tsmn is zero after whole years)
   CK(cudaMemsetAsync(h->d_acc, 0, (size_t)h->n_members * GA_COUNT * GNC * 4, h->stream));
   CK(cudaStreamSynchronize(h->stream));
@@ -489,8 +522,40 @@ extern "C" int greb_b200_reset_scenario(greb_b200_t h) {
   return GREB_OK;
 }
 
-extern "C" int greb_b200_run(greb_b200_t h, int years, float* out, const int* out_members, int n_out, float* gmean,
-                             float* gmean_coslat) {
+// Completes a greb_b200_run_async: both streams drained, the annual diagnostics scattered from the pinned
+// mirror into the caller's arrays.  Every entry point that touches device state calls it first, so a
+// forgotten greb_b200_wait cannot race with anything.
+static int finish_pending(greb_b200_t h) {
+  if (!h->pending) return GREB_OK;
+  h->pending = false;
+  cudaError_t e1 = cudaStreamSynchronize(h->stream);
+  cudaError_t e2 = cudaStreamSynchronize(h->copy_stream);
+  h->copy_pending[0] = h->copy_pending[1] = false;
+  if (e1 != cudaSuccess || e2 != cudaSuccess) {
+    h->err = std::string("greb_b200_wait: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2);
+    return GREB_E_CUDA;
+  }
+  cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1);
+  const int N = h->n_members, Y = h->pend_years;
+  if (h->pend_gmean || h->pend_gcos)
+    for (int y = 0; y < Y; ++y)
+      for (int m = 0; m < N; ++m) {
+        const float* d = h->h_diag_hist + ((size_t)y * N + m) * 2;
+        if (h->pend_gmean) h->pend_gmean[(size_t)m * Y + y] = d[0];
+        if (h->pend_gcos) h->pend_gcos[(size_t)m * Y + y] = d[1];
+      }
+  h->pend_gmean = h->pend_gcos = nullptr;
+  return GREB_OK;
+}
+
+extern "C" int greb_b200_wait(greb_b200_t h) {
+  if (!h) return GREB_E_INVALID;
+  cudaSetDevice(h->device);
+  return finish_pending(h);
+}
+
+extern "C" int greb_b200_run_async(greb_b200_t h, int years, float* out, const int* out_members, int n_out,
+                                   float* gmean, float* gmean_coslat) {
   if (!h) return GREB_E_INVALID;
   if (!h->inited) return fail(h, GREB_E_INVALID, "greb_b200_run: greb_b200_init has not been called");
   if (years < 0) return fail(h, GREB_E_INVALID, "greb_b200_run: years < 0");
@@ -500,25 +565,52 @@ extern "C" int greb_b200_run(greb_b200_t h, int years, float* out, const int* ou
   if (y_first + years > h->co2_stride)
     return fail(h, GREB_E_INVALID, "greb_b200_run: the CO2 paths given to set_member are shorter than the run");
   if (!out_members) n_out = N;
+  // every argument is checked BEFORE the first launch: a failed call leaves the calendar and the device untouched
+  if (out_members) {
+    if (n_out < 0) return fail(h, GREB_E_INVALID, "greb_b200_run: n_out < 0");
+    for (int i = 0; i < n_out; ++i)
+      if (out_members[i] < 0 || out_members[i] >= N)
+        return fail(h, GREB_E_INVALID, "greb_b200_run: out_members entry out of range");
+  }
   cudaSetDevice(h->device);
+  // A call still in flight keeps its kernels and copies; only its host-side completion (diagnostics
+  // scatter) must happen before the pinned mirror is reused.  The copies of its last years go on
+  // overlapping this call's kernels: that is the point of the asynchronous entry.
+  const bool want_diag = gmean || gmean_coslat;
+  if (h->pending && (want_diag || h->pend_gmean || h->pend_gcos)) {
+    const int rc = finish_pending(h);
+    if (rc != GREB_OK) return rc;
+  }
+  const bool chained = h->pending;   // true: the previous async call's copies may still be running
+  if (want_diag && years > h->hist_years) {
+    if (h->d_diag_hist) cudaFree(h->d_diag_hist);
+    if (h->h_diag_hist) cudaFreeHost(h->h_diag_hist);
+    h->d_diag_hist = h->h_diag_hist = nullptr;
+    h->hist_years = 0;
+    CK(cudaMalloc((void**)&h->d_diag_hist, (size_t)years * N * 2 * 4));
+    CK(cudaMallocHost((void**)&h->h_diag_hist, (size_t)years * N * 2 * 4));
+    h->hist_years = years;
+  }
   GrebKernelArgs a = base_args(h);
   a.spinup = 0;
   const size_t year_floats = (size_t)12 * 5 * GNC;
-  std::vector<float> diag((size_t)N * 2);
   h->last_launches = 0;
-  CK(cudaEventRecord(h->ev0, h->stream));
+  if (!chained) CK(cudaEventRecord(h->ev0, h->stream));
   for (int y = 0; y < years; ++y) {
-    const int b = y & 1;
+    const int b = (int)(h->year_seq & 1);
     a.it0 = h->it_next;
     a.nsteps = GNT;
     a.out = h->d_out[b];
-    if (y >= 2 && out) CK(cudaStreamWaitEvent(h->stream, h->ev_c[b], 0));  // buffer b free again
+    if (h->copy_pending[b]) CK(cudaStreamWaitEvent(h->stream, h->ev_c[b], 0));  // buffer b free again
     launch_member(h, N, a);
     h->last_launches++;
     CK(cudaGetLastError());
     h->it_next += GNT;
+    h->year_seq++;
     h->last_out = b;
-    if (y == years - 1) CK(cudaEventRecord(h->ev1, h->stream));
+    if (want_diag)   // the year's diagnostics stay on the device; ONE pinned copy at the end of the call
+      CK(cudaMemcpyAsync(h->d_diag_hist + (size_t)y * N * 2, h->d_diag, (size_t)N * 2 * 4, cudaMemcpyDeviceToDevice,
+                         h->stream));
     if (out) {
       CK(cudaEventRecord(h->ev_k[b], h->stream));
       CK(cudaStreamWaitEvent(h->copy_stream, h->ev_k[b], 0));
@@ -526,54 +618,68 @@ extern "C" int greb_b200_run(greb_b200_t h, int years, float* out, const int* ou
         CK(cudaMemcpy2DAsync(out + (size_t)y * year_floats, (size_t)years * year_floats * 4, h->d_out[b],
                              year_floats * 4, year_floats * 4, N, cudaMemcpyDeviceToHost, h->copy_stream));
       } else {
-        for (int i = 0; i < n_out; ++i) {
-          const int m = out_members[i];
-          if (m < 0 || m >= N) return fail(h, GREB_E_INVALID, "greb_b200_run: out_members entry out of range");
-          CK(cudaMemcpyAsync(out + ((size_t)i * years + y) * year_floats, h->d_out[b] + (size_t)m * year_floats,
-                             year_floats * 4, cudaMemcpyDeviceToHost, h->copy_stream));
-        }
+        for (int i = 0; i < n_out; ++i)
+          CK(cudaMemcpyAsync(out + ((size_t)i * years + y) * year_floats,
+                             h->d_out[b] + (size_t)out_members[i] * year_floats, year_floats * 4,
+                             cudaMemcpyDeviceToHost, h->copy_stream));
       }
       CK(cudaEventRecord(h->ev_c[b], h->copy_stream));
-    }
-    if (gmean || gmean_coslat) {
-      CK(cudaMemcpyAsync(diag.data(), h->d_diag, diag.size() * 4, cudaMemcpyDeviceToHost, h->stream));
-      CK(cudaStreamSynchronize(h->stream));
-      for (int m = 0; m < N; ++m) {
-        if (gmean) gmean[(size_t)m * years + y] = diag[(size_t)m * 2];
-        if (gmean_coslat) gmean_coslat[(size_t)m * years + y] = diag[(size_t)m * 2 + 1];
-      }
+      h->copy_pending[b] = true;
     }
   }
-  if (years == 0) CK(cudaEventRecord(h->ev1, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
-  CK(cudaStreamSynchronize(h->copy_stream));
-  CK(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+  CK(cudaEventRecord(h->ev1, h->stream));
+  if (want_diag && years > 0)
+    CK(cudaMemcpyAsync(h->h_diag_hist, h->d_diag_hist, (size_t)years * N * 2 * 4, cudaMemcpyDeviceToHost, h->stream));
+  h->pending = true;
+  h->pend_years = years;
+  h->pend_gmean = gmean;
+  h->pend_gcos = gmean_coslat;
   return GREB_OK;
 }
 
-extern "C" int greb_b200_time_loop(greb_b200_t h, int it) {
+extern "C" int greb_b200_run(greb_b200_t h, int years, float* out, const int* out_members, int n_out, float* gmean,
+                             float* gmean_coslat) {
   if (!h) return GREB_E_INVALID;
-  if (!h->inited) return fail(h, GREB_E_INVALID, "greb_b200_time_loop: not initialised");
-  if (it < 1 || (it - 1) / GNT >= h->co2_stride) return fail(h, GREB_E_INVALID, "greb_b200_time_loop: bad it");
   cudaSetDevice(h->device);
+  int rc = finish_pending(h);
+  if (rc != GREB_OK) return rc;
+  rc = greb_b200_run_async(h, years, out, out_members, n_out, gmean, gmean_coslat);
+  if (rc != GREB_OK) return rc;
+  return finish_pending(h);
+}
+
+extern "C" int greb_b200_time_steps(greb_b200_t h, int it0, int nsteps) {
+  if (!h) return GREB_E_INVALID;
+  if (!h->inited) return fail(h, GREB_E_INVALID, "greb_b200_time_steps: not initialised");
+  if (it0 < 1 || nsteps < 1 || nsteps > GNT || (it0 + nsteps - 2) / GNT >= h->co2_stride)
+    return fail(h, GREB_E_INVALID, "greb_b200_time_steps: bad step range (1 <= nsteps <= 730, inside the CO2 path)");
+  cudaSetDevice(h->device);
+  FIN(h);
   GrebKernelArgs a = base_args(h);
   a.spinup = 0;
-  a.it0 = it;
-  a.nsteps = 1;
-  a.out = h->d_out[0];
+  a.it0 = it0;
+  a.nsteps = nsteps;
+  a.out = h->d_out[0];   // at most 12 month ends in 730 steps: they fill slots 0.. of the year buffer
   h->last_out = 0;
+  CK(cudaEventRecord(h->ev0, h->stream));
   launch_member(h, h->n_members, a);
+  CK(cudaEventRecord(h->ev1, h->stream));
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(h->stream));
-  h->it_next = it + 1;
+  CK(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+  h->last_launches = 1;
+  h->it_next = it0 + nsteps;
   return GREB_OK;
 }
+
+extern "C" int greb_b200_time_loop(greb_b200_t h, int it) { return greb_b200_time_steps(h, it, 1); }
 
 extern "C" int greb_b200_get_state(greb_b200_t h, int member, int which, float* out) {
   if (!h) return GREB_E_INVALID;
   if (!h->inited || member < 0 || member >= h->n_members || which < 0 || which >= GS_COUNT || !out)
     return fail(h, GREB_E_INVALID, "greb_b200_get_state: bad arguments");
   cudaSetDevice(h->device);
+  FIN(h);
   CK(cudaMemcpy(out, h->d_state + ((size_t)member * GS_COUNT + which) * GNC, GNC * 4, cudaMemcpyDeviceToHost));
   return GREB_OK;
 }
@@ -583,6 +689,7 @@ extern "C" int greb_b200_set_state(greb_b200_t h, int member, int which, const f
   if (!h->inited || member < 0 || member >= h->n_members || which < 0 || which >= GS_COUNT || !in)
     return fail(h, GREB_E_INVALID, "greb_b200_set_state: bad arguments");
   cudaSetDevice(h->device);
+  FIN(h);
   CK(cudaMemcpy(h->d_state + ((size_t)member * GS_COUNT + which) * GNC, in, GNC * 4, cudaMemcpyHostToDevice));
   return GREB_OK;
 }
@@ -591,6 +698,7 @@ extern "C" int greb_b200_get_states(greb_b200_t h, float* out) {
   if (!h) return GREB_E_INVALID;
   if (!h->inited || !out) return fail(h, GREB_E_INVALID, "greb_b200_get_states: bad arguments");
   cudaSetDevice(h->device);
+  FIN(h);
   CK(cudaMemcpyAsync(out, h->d_state, (size_t)h->n_members * GS_COUNT * GNC * 4, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   return GREB_OK;
@@ -600,6 +708,7 @@ extern "C" int greb_b200_set_states(greb_b200_t h, const float* in) {
   if (!h) return GREB_E_INVALID;
   if (!h->inited || !in) return fail(h, GREB_E_INVALID, "greb_b200_set_states: bad arguments");
   cudaSetDevice(h->device);
+  FIN(h);
   CK(cudaMemcpyAsync(h->d_state, in, (size_t)h->n_members * GS_COUNT * GNC * 4, cudaMemcpyHostToDevice, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   return GREB_OK;
@@ -610,6 +719,7 @@ extern "C" int greb_b200_get_fluxcorr(greb_b200_t h, int member, int which, floa
   if (!h->inited || member < 0 || member >= h->n_members || which < 0 || which > 2 || !out)
     return fail(h, GREB_E_INVALID, "greb_b200_get_fluxcorr: bad arguments");
   cudaSetDevice(h->device);
+  FIN(h);
   static const int sel[3] = {GC_TF, GC_QF, GC_TOF};  // ABI order: TF, qF, ToF
   const float* base = h->d_corr + (size_t)h->group_of[member] * GNT * GC_COUNT * GNC + (size_t)sel[which] * GNC;
   CK(cudaMemcpy2D(out, GNC * 4, base, (size_t)GC_COUNT * GNC * 4, GNC * 4, GNT, cudaMemcpyDeviceToHost));
@@ -621,6 +731,7 @@ extern "C" int greb_b200_set_fluxcorr(greb_b200_t h, int member, int which, cons
   if (!h->inited || member < 0 || member >= h->n_members || which < 0 || which > 2 || !in)
     return fail(h, GREB_E_INVALID, "greb_b200_set_fluxcorr: bad arguments");
   cudaSetDevice(h->device);
+  FIN(h);
   static const int sel[3] = {GC_TF, GC_QF, GC_TOF};  // ABI order: TF, qF, ToF
   float* base = h->d_corr + (size_t)h->group_of[member] * GNT * GC_COUNT * GNC + (size_t)sel[which] * GNC;
   CK(cudaMemcpy2D(base, (size_t)GC_COUNT * GNC * 4, in, GNC * 4, GNC * 4, GNT, cudaMemcpyHostToDevice));
@@ -632,6 +743,7 @@ extern "C" int greb_b200_get_monthly(greb_b200_t h, int member, float* out) {
   if (!h->inited || member < 0 || member >= h->n_members || !out)
     return fail(h, GREB_E_INVALID, "greb_b200_get_monthly: bad arguments");
   cudaSetDevice(h->device);
+  FIN(h);
   CK(cudaMemcpy(out, h->d_out[h->last_out] + (size_t)member * 12 * 5 * GNC, (size_t)12 * 5 * GNC * 4,
                 cudaMemcpyDeviceToHost));
   return GREB_OK;
@@ -649,6 +761,7 @@ extern "C" int greb_b200_get_flags(greb_b200_t h, int* flags) {
   if (!h) return GREB_E_INVALID;
   if (!h->inited || !flags) return fail(h, GREB_E_INVALID, "greb_b200_get_flags: bad arguments");
   cudaSetDevice(h->device);
+  FIN(h);
   CK(cudaMemcpy(flags, h->d_flags, (size_t)h->n_members * 4, cudaMemcpyDeviceToHost));
   return GREB_OK;
 }
@@ -660,6 +773,7 @@ extern "C" int greb_b200_circulation(greb_b200_t h, int member, int ityr, const 
       n < 1)
     return fail(h, GREB_E_INVALID, "greb_b200_circulation: bad arguments");
   cudaSetDevice(h->device);
+  FIN(h);
   float *dX = nullptr, *dW = nullptr, *dO = nullptr;
   const size_t bytes = (size_t)n * GNC * 4;
   CK(cudaMalloc((void**)&dX, bytes));
@@ -687,6 +801,75 @@ extern "C" int greb_b200_circulation(greb_b200_t h, int member, int ityr, const 
   cudaFree(dO);
   return GREB_OK;
 }
+
+// ---- asynchronous state transfers + compute-stream sync (pipelined host loops, bench.py e2e) -----
+extern "C" int greb_b200_set_states_async(greb_b200_t h, const float* in) {
+  if (!h) return GREB_E_INVALID;
+  if (!h->inited || !in) return fail(h, GREB_E_INVALID, "greb_b200_set_states_async: bad arguments");
+  cudaSetDevice(h->device);
+  CK(cudaMemcpyAsync(h->d_state, in, (size_t)h->n_members * GS_COUNT * GNC * 4, cudaMemcpyHostToDevice, h->stream));
+  return GREB_OK;
+}
+
+extern "C" int greb_b200_get_states_async(greb_b200_t h, float* out) {
+  if (!h) return GREB_E_INVALID;
+  if (!h->inited || !out) return fail(h, GREB_E_INVALID, "greb_b200_get_states_async: bad arguments");
+  cudaSetDevice(h->device);
+  CK(cudaMemcpyAsync(out, h->d_state, (size_t)h->n_members * GS_COUNT * GNC * 4, cudaMemcpyDeviceToHost, h->stream));
+  return GREB_OK;
+}
+
+extern "C" int greb_b200_sync_compute(greb_b200_t h) {
+  if (!h) return GREB_E_INVALID;
+  cudaSetDevice(h->device);
+  CK(cudaStreamSynchronize(h->stream));
+  return GREB_OK;
+}
+
+// ---- checkpoint / resume of a scenario (src/greb.f90:226-234 loop state) ------------
+// The loop state of the reference is Ts1,Ta1,To1,q1 + cap_surf (get/set_states), the calendar
+// (it -> ityr, jday, mon, year, irec are all functions of `it`, src/greb.f90:241-252, 975-985) and the
+// accumulators Tmm,Tamm,Tomm,qmm,apmm (:149) + tsmn (:145).
+extern "C" int greb_b200_get_calendar(greb_b200_t h, int* it_next) {
+  if (!h) return GREB_E_INVALID;
+  if (!h->inited || !it_next) return fail(h, GREB_E_INVALID, "greb_b200_get_calendar: bad arguments");
+  cudaSetDevice(h->device);
+  FIN(h);
+  *it_next = h->it_next;
+  return GREB_OK;
+}
+
+extern "C" int greb_b200_set_calendar(greb_b200_t h, int it_next) {
+  if (!h) return GREB_E_INVALID;
+  if (!h->inited || it_next < 1) return fail(h, GREB_E_INVALID, "greb_b200_set_calendar: bad arguments");
+  if ((it_next - 1) / GNT > h->co2_stride)
+    return fail(h, GREB_E_INVALID, "greb_b200_set_calendar: beyond the CO2 paths given to set_member");
+  cudaSetDevice(h->device);
+  FIN(h);
+  h->it_next = it_next;
+  return GREB_OK;
+}
+
+extern "C" int greb_b200_get_accumulators(greb_b200_t h, float* out) {
+  if (!h) return GREB_E_INVALID;
+  if (!h->inited || !out) return fail(h, GREB_E_INVALID, "greb_b200_get_accumulators: bad arguments");
+  cudaSetDevice(h->device);
+  FIN(h);
+  CK(cudaMemcpyAsync(out, h->d_acc, (size_t)h->n_members * GA_COUNT * GNC * 4, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return GREB_OK;
+}
+
+extern "C" int greb_b200_set_accumulators(greb_b200_t h, const float* in) {
+  if (!h) return GREB_E_INVALID;
+  if (!h->inited || !in) return fail(h, GREB_E_INVALID, "greb_b200_set_accumulators: bad arguments");
+  cudaSetDevice(h->device);
+  FIN(h);
+  CK(cudaMemcpyAsync(h->d_acc, in, (size_t)h->n_members * GA_COUNT * GNC * 4, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return GREB_OK;
+}
+
 
 extern "C" int greb_b200_last_kernel_ms(greb_b200_t h, float* ms, int* launches) {
   if (!h) return GREB_E_INVALID;

@@ -107,7 +107,9 @@ def _values(text: str):
 
 def parse_namelist(text: str) -> Dict[str, Dict[str, list]]:
     """{group: {name: [values]}} — group and variable names lower-cased, `! comments`, `&G ... /`
-    (or `&end`), `a = 1, 2, 3`, `(/ .. /)`, repeat counts, quoted strings, empty groups."""
+    (or `&end`), `a = 1, 2, 3`, `(/ .. /)`, repeat counts, quoted strings (which may contain `=`),
+    empty groups, subscripted assignments `a(3) = 5, 6` (elements 3 and 4; unassigned positions of the
+    returned list are None)."""
     body = "\n".join(_strip_comment(ln) for ln in text.splitlines())
     groups: Dict[str, Dict[str, list]] = {}
     pos = 0
@@ -135,12 +137,32 @@ def parse_namelist(text: str) -> Dict[str, Dict[str, list]]:
         if end is None:
             raise NamelistError(f"namelist group &{name} is not terminated by '/'")
         content = body[start:end]
-        items: Dict[str, list] = {}
-        # split "name = values" pairs: a new pair starts at an identifier followed by '='
-        pairs = list(re.finditer(r"([A-Za-z_]\w*)\s*(\(\s*\d+\s*\))?\s*=", content))
+        # text inside quotes can hold anything ("a = b", "x(1)"): blank it for the pair search only
+        masked, q = [], None
+        for ch in content:
+            if q:
+                masked.append(q if ch == q else "_")
+                if ch == q:
+                    q = None
+            else:
+                if ch in "'\"":
+                    q = ch
+                masked.append(ch)
+        masked = "".join(masked)
+        # split "name = values" / "name(i) = values" pairs: a new pair starts at an identifier followed by '='
+        pairs = list(re.finditer(r"([A-Za-z_]\w*)\s*(?:\(\s*(\d+)\s*\))?\s*=", masked))
+        slots: Dict[str, Dict[int, object]] = {}
         for j, pm in enumerate(pairs):
             v_end = pairs[j + 1].start() if j + 1 < len(pairs) else len(content)
-            items[pm.group(1).lower()] = _values(content[pm.end():v_end])
+            vals = _values(content[pm.end():v_end])
+            first = int(pm.group(2)) - 1 if pm.group(2) else 0         # name(i) = v1, v2 fills i, i+1, ...
+            if first < 0:
+                raise NamelistError(f"{pm.group(1)}({pm.group(2)}): subscripts start at 1")
+            d = slots.setdefault(pm.group(1).lower(), {})
+            for k, v in enumerate(vals):
+                d[first + k] = v
+        # positions never assigned stay None (the variable keeps its previous value there)
+        items: Dict[str, list] = {n: [d.get(i) for i in range(max(d) + 1)] if d else [] for n, d in slots.items()}
         if name in groups:
             raise NamelistError(f"namelist group &{name} appears twice")
         groups[name] = items
@@ -183,6 +205,13 @@ def pad_co2(given: Sequence[float], n_years: int) -> np.ndarray:
     return co2
 
 
+def _only(name: str, v: list):
+    """the value of a scalar namelist variable (a subscript or several values are errors in Fortran too)"""
+    if len(v) != 1 or v[0] is None:
+        raise NamelistError(f"{name} is a scalar: exactly one value, no subscript")
+    return v[0]
+
+
 def config_from_namelist(text: str, defaults: "_lib.Physics | None" = None) -> RunConfig:
     """The four groups of greb.f90 (`physics_par`, `numerics_par`, `diagnostics_par`, `co2_par`); a
     missing group keeps its defaults (the reference requires all four to be present, f:1042-1050)."""
@@ -197,26 +226,27 @@ def config_from_namelist(text: str, defaults: "_lib.Physics | None" = None) -> R
             if len(v) > 10:
                 raise NamelistError("p_emi has 10 elements")
             for i, x in enumerate(v):
-                p.p_emi[i] = float(x)
+                if x is not None:
+                    p.p_emi[i] = float(x)
         elif k in _PHYS:
-            setattr(p, _PHYS[k], float(v[0]))
+            setattr(p, _PHYS[k], float(_only(k, v)))
         else:
             raise NamelistError(f"physics_par: unknown variable {k}")
     cfg = RunConfig(physics=p)
     for k, v in g.get("numerics_par", {}).items():
         if k not in ("ipx", "ipy", "time_flux", "time_scnr", "year0"):
             raise NamelistError(f"numerics_par: unknown variable {k}")
-        setattr(cfg, k, int(v[0]))
+        setattr(cfg, k, int(_only(k, v)))
     for k, v in g.get("diagnostics_par", {}).items():
         if k not in ("output_file", "ens_id"):
             raise NamelistError(f"diagnostics_par: unknown variable {k}")
-        setattr(cfg, k, str(v[0]))
+        setattr(cfg, k, str(_only(k, v)))
     given = []
     for k, v in g.get("co2_par", {}).items():
         if k == "co2_flux":
-            p.co2_flux = float(v[0])
+            p.co2_flux = float(_only(k, v))
         elif k == "co2_ppm":
-            given = [float(x) for x in v]
+            given = [-1.0 if x is None else float(x) for x in v]   # co2_ppm(:) = -1 before the read, f:1047
         else:
             raise NamelistError(f"co2_par: unknown variable {k}")
     if len(given) > max(cfg.time_scnr, 0):
@@ -514,3 +544,42 @@ def load_spinup(path: str, ens: "_lib.Ensemble", members: Sequence[int], key: st
         for i, n in enumerate(_lib.STATE):
             ens.set_state(m, n, state[i])
     return True
+
+
+# ------------------------------------------------------------------------------------------------
+# checkpoint / resume of a scenario (loop state of f:226-234)
+# ------------------------------------------------------------------------------------------------
+def save_checkpoint(path: str, ens: "_lib.Ensemble", with_fluxcorr: bool = True) -> None:
+    """Everything `greb_model`'s scenario loop carries from one step to the next, for every member of
+    the handle: Ts1,Ta1,To1,q1,cap_surf, the step counter `it` of the next step (mon, year, irec, ityr,
+    jday are functions of it, f:241-252, 975-985), the monthly accumulators and tsmn (f:145-149) — plus,
+    unless `with_fluxcorr` is False, the three flux-correction fields of every physics group (40.4 MB
+    each; a member's corrections are read through the member itself).  Written atomically as .npz."""
+    d = {"version": np.array(1), "n_members": np.array(ens.n), "it_next": np.array(ens.get_calendar()),
+         "state": ens.get_states(), "acc": ens.get_accumulators()}
+    if with_fluxcorr:
+        for w, name in enumerate(("tf_correct", "qf_correct", "tof_correct")):
+            d[name] = np.stack([ens.get_fluxcorr(m, w) for m in range(ens.n)])
+    os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+    tmp = path + ".tmp.npz"
+    np.savez(tmp, **d)
+    os.replace(tmp, path)
+
+
+def load_checkpoint(path: str, ens: "_lib.Ensemble") -> int:
+    """Restore a checkpoint into an INITIALISED handle with the same members (same set_member calls:
+    physics and CO2 paths are configuration, not state).  Returns the step counter `it` of the next step;
+    continue with `ens.run(years)` (at a year boundary) or `ens.time_steps(it, n)` to the next one."""
+    with np.load(path) as z:
+        if int(z["version"]) != 1 or int(z["n_members"]) != ens.n:
+            raise ValueError(f"{path}: checkpoint of {int(z['n_members'])} members, handle has {ens.n}")
+        ens.set_states(z["state"])
+        ens.set_accumulators(z["acc"])
+        if "tf_correct" in z.files:
+            for w, name in enumerate(("tf_correct", "qf_correct", "tof_correct")):
+                a = z[name]
+                for m in range(ens.n):
+                    ens.set_fluxcorr(m, w, a[m])
+        it = int(z["it_next"])
+    ens.set_calendar(it)
+    return it

@@ -27,7 +27,10 @@ ABI_SYMBOLS = ["greb_b200_physics_defaults", "greb_b200_physics_original", "greb
                "greb_b200_run", "greb_b200_time_loop", "greb_b200_get_state", "greb_b200_set_state",
                "greb_b200_get_states", "greb_b200_set_states",
                "greb_b200_get_fluxcorr", "greb_b200_set_fluxcorr", "greb_b200_get_monthly", "greb_b200_diag_device", "greb_b200_get_flags",
-               "greb_b200_circulation", "greb_b200_last_kernel_ms"]
+               "greb_b200_circulation", "greb_b200_last_kernel_ms",
+               "greb_b200_run_async", "greb_b200_wait", "greb_b200_time_steps", "greb_b200_set_states_async",
+               "greb_b200_get_states_async", "greb_b200_sync_compute", "greb_b200_get_calendar",
+               "greb_b200_set_calendar", "greb_b200_get_accumulators", "greb_b200_set_accumulators"]
 
 
 class Physics(C.Structure):
@@ -93,7 +96,17 @@ def load_library():
     L.greb_b200_spinup.argtypes = [vp, C.c_int]
     L.greb_b200_reset_scenario.argtypes = [vp]
     L.greb_b200_run.argtypes = [vp, C.c_int, vp, ip, C.c_int, fp, fp]
+    L.greb_b200_run_async.argtypes = [vp, C.c_int, vp, ip, C.c_int, fp, fp]
+    L.greb_b200_wait.argtypes = [vp]
     L.greb_b200_time_loop.argtypes = [vp, C.c_int]
+    L.greb_b200_time_steps.argtypes = [vp, C.c_int, C.c_int]
+    L.greb_b200_set_states_async.argtypes = [vp, vp]
+    L.greb_b200_get_states_async.argtypes = [vp, vp]
+    L.greb_b200_sync_compute.argtypes = [vp]
+    L.greb_b200_get_calendar.argtypes = [vp, ip]
+    L.greb_b200_set_calendar.argtypes = [vp, C.c_int]
+    L.greb_b200_get_accumulators.argtypes = [vp, vp]
+    L.greb_b200_set_accumulators.argtypes = [vp, vp]
     L.greb_b200_get_state.argtypes = [vp, C.c_int, C.c_int, fp]
     L.greb_b200_set_state.argtypes = [vp, C.c_int, C.c_int, fp]
     L.greb_b200_get_states.argtypes = [vp, vp]
@@ -228,8 +241,55 @@ class Ensemble:
         self._ck(rc, "greb_b200_run")
         self.years_run += years
 
+    def run_async(self, years: int, out_ptr=None, out_members=None):
+        """greb_b200_run_async: enqueue `years` years and return; records go to the host address `out_ptr`
+        (pinned memory, valid until the next wait()).  No diagnostics arrays: read diag_device() or call run()."""
+        om = None if out_members is None else np.ascontiguousarray(out_members, dtype=np.int32)
+        n_out = self.n if om is None else len(om)
+        rc = self.L.greb_b200_run_async(self.h, years, C.c_void_p(out_ptr) if out_ptr else None,
+                                        om.ctypes.data_as(C.POINTER(C.c_int)) if om is not None else None, n_out,
+                                        None, None)
+        self._ck(rc, "greb_b200_run_async")
+        self._keep_om = om
+        self.years_run += years
+
+    def wait(self):
+        self._ck(self.L.greb_b200_wait(self.h), "greb_b200_wait")
+
+    def sync_compute(self):
+        self._ck(self.L.greb_b200_sync_compute(self.h), "greb_b200_sync_compute")
+
+    def set_states_async(self, ptr: int):
+        self._ck(self.L.greb_b200_set_states_async(self.h, C.c_void_p(ptr)), "greb_b200_set_states_async")
+
+    def get_states_async(self, ptr: int):
+        self._ck(self.L.greb_b200_get_states_async(self.h, C.c_void_p(ptr)), "greb_b200_get_states_async")
+
     def time_loop(self, it: int):
         self._ck(self.L.greb_b200_time_loop(self.h, it), "greb_b200_time_loop")
+
+    def time_steps(self, it0: int, nsteps: int):
+        """`nsteps` (<= 730) consecutive time_loop calls it0, it0+1, ... in one launch"""
+        self._ck(self.L.greb_b200_time_steps(self.h, it0, nsteps), "greb_b200_time_steps")
+
+    # ---- checkpoint / resume (include/greb_b200.h) ----
+    def get_calendar(self) -> int:
+        it = C.c_int()
+        self._ck(self.L.greb_b200_get_calendar(self.h, C.byref(it)), "greb_b200_get_calendar")
+        return it.value
+
+    def set_calendar(self, it_next: int):
+        self._ck(self.L.greb_b200_set_calendar(self.h, int(it_next)), "greb_b200_set_calendar")
+
+    def get_accumulators(self) -> np.ndarray:
+        a = np.zeros((self.n, 6, YD, XD), dtype=np.float32)
+        self._ck(self.L.greb_b200_get_accumulators(self.h, C.c_void_p(a.ctypes.data)), "greb_b200_get_accumulators")
+        return a
+
+    def set_accumulators(self, a):
+        a = _f(a)
+        assert a.shape == (self.n, 6, YD, XD)
+        self._ck(self.L.greb_b200_set_accumulators(self.h, C.c_void_p(a.ctypes.data)), "greb_b200_set_accumulators")
 
     def get_state(self, m: int, name: str) -> np.ndarray:
         a = np.zeros((YD, XD), dtype=np.float32)

@@ -145,9 +145,24 @@ int greb_b200_reset_scenario(greb_b200_t h);
 int greb_b200_run(greb_b200_t h, int years, float* out, const int* out_members, int n_out, float* gmean,
                   float* gmean_coslat);
 
+/* The same loop without blocking the host: greb_b200_run_async enqueues the years (kernels on the
+ * handle's compute stream, the device->host copies of each year's records on its copy stream) and
+ * returns; greb_b200_wait blocks until everything enqueued so far is complete and only then fills
+ * gmean / gmean_coslat (from a pinned mirror: no host synchronisation per simulated year).  Calls may
+ * be chained: a second run_async issued before the wait starts its kernels while the previous call's
+ * records are still being copied — `out` of a call must stay valid (and should be pinned) until the
+ * next greb_b200_wait.  greb_b200_run == run_async + wait.  Every other entry point that touches the
+ * device state waits implicitly first. */
+int greb_b200_run_async(greb_b200_t h, int years, float* out, const int* out_members, int n_out, float* gmean,
+                        float* gmean_coslat);
+int greb_b200_wait(greb_b200_t h);
+
 /* One time_loop call (src/greb.f90:239-274) for every member with step counter `it` (1-based,
- * as the reference's `it`).  Test entry: lets a host drive the loop step by step. */
+ * as the reference's `it`).  Test entry: lets a host drive the loop step by step.
+ * greb_b200_time_steps: `nsteps` (<= 730) consecutive calls it0, it0+1, ... in one launch — how a
+ * host continues from a mid-year checkpoint to the next year boundary (greb_b200_run needs one). */
 int greb_b200_time_loop(greb_b200_t h, int it);
+int greb_b200_time_steps(greb_b200_t h, int it0, int nsteps);
 
 /* ---- state / results access ---------------------------------------------------------------- */
 
@@ -157,6 +172,22 @@ int greb_b200_set_state(greb_b200_t h, int member, int which, const float* in);
 /* bulk variants: all members at once, [n_members][5][48][96] in the order of the enum above */
 int greb_b200_get_states(greb_b200_t h, float* out);
 int greb_b200_set_states(greb_b200_t h, const float* in);
+/* Pipelined host loops: the same transfers enqueued on the handle's compute stream without waiting
+ * (ordered with the kernels of run_async); greb_b200_sync_compute waits for that stream only, so
+ * record copies of earlier years keep running on the copy stream.  Host buffers should be pinned. */
+int greb_b200_set_states_async(greb_b200_t h, const float* in);
+int greb_b200_get_states_async(greb_b200_t h, float* out);
+int greb_b200_sync_compute(greb_b200_t h);
+/* Checkpoint / resume of a scenario.  The reference keeps its loop state in the module arrays
+ * Ts1,Ta1,To1,q1 (+cap_surf), the counters it/year/mon/irec — all functions of `it`
+ * (src/greb.f90:226-234, 241-252, 975-985) — and the accumulators Tmm,Tamm,Tomm,qmm,apmm (:149) and
+ * tsmn (:145).  get/set_states + get/set_calendar (`it_next` = the `it` of the next step, 1-based)
+ * + get/set_accumulators ([n_members][6][48][96] in that order) save and restore all of it; with the
+ * flux corrections (get/set_fluxcorr) a fresh handle continues a run bit for bit. */
+int greb_b200_get_calendar(greb_b200_t h, int* it_next);
+int greb_b200_set_calendar(greb_b200_t h, int it_next);
+int greb_b200_get_accumulators(greb_b200_t h, float* out);
+int greb_b200_set_accumulators(greb_b200_t h, const float* in);
 /* which: 0 = TF_correct, 1 = qF_correct, 2 = ToF_correct (src/greb.f90:110), out [730][48][96] */
 int greb_b200_get_fluxcorr(greb_b200_t h, int member, int which, float* out);
 /* Restores flux corrections saved with greb_b200_get_fluxcorr (a spin-up cache: together with

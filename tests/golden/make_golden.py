@@ -73,6 +73,24 @@ def kernel_kats(f, R, seed=7):
             d[f"k{case}_{nm}_advection"] = aa
             d[f"k{case}_{nm}_circulation"] = cc
         d[f"k{case}_meta"] = np.array([ityr, kappa], dtype=np.float64)
+    # case 4: mixed-sign anomaly fields — the only inputs on which where(d <= -T) d = -0.9*T (f:715, f:907)
+    # fires (on positive fields the stable sub-step never removes more than a cell holds)
+    case, ityr, kappa = 4, 213, 8e5
+    R.set_physics(kappa=kappa)
+    R.seti("ityr", ityr)
+    T = rng.normal(0.0, 1.0, (48, 96)).astype(np.float32)
+    q = (rng.normal(0.0, 1.0, (48, 96)) * 1e-3).astype(np.float32)
+    wza = np.exp(-f.z_topo / np.float32(8400.0)).astype(np.float32)
+    wzv = np.exp(-f.z_topo / np.float32(5000.0)).astype(np.float32)
+    for nm, X, wz in (("T", T, wza), ("q", q, wzv)):
+        dd, aa, cc = z(), z(), z()
+        R.call("diffusion", X, dd, 8400.0, wz)
+        R.call("advection", X, aa, 8400.0, wz)
+        R.call("circulation", X, cc, 8400.0, wz)
+        d[f"k{case}_{nm}_in"], d[f"k{case}_{nm}_wz"] = X, wz
+        d[f"k{case}_{nm}_diffusion"], d[f"k{case}_{nm}_advection"], d[f"k{case}_{nm}_circulation"] = dd, aa, cc
+    d[f"k{case}_meta"] = np.array([ityr, kappa], dtype=np.float64)
+    d["n_cases"] = np.array(5)
     R.set_physics(kappa=8e5)
     return d
 
@@ -88,6 +106,8 @@ def main():
     kd["forcing_digest"] = np.array(digest)
     np.savez_compressed(os.path.join(HERE, "ref_kernels.npz"), **kd)
     print("ref_kernels.npz", len(kd))
+    if sys.argv[1:] == ["kernels"]:
+        return
 
     # ---- config 1: default namelist (3 yr flux correction + 50 yr at 680 ppm from 1940) ---------
     R = ref.Ref.fresh("greb")

@@ -45,7 +45,7 @@ def test_fixtures_match_the_synthetic_forcing(forcing):
 
 def test_kernels_bit_exact(oracle_mod, forcing):
     g = load("ref_kernels.npz")
-    for case in range(4):
+    for case in range(int(g["n_cases"])):
         ityr, kappa = g[f"k{case}_meta"]
         o = oracle_mod.Oracle(forcing, kappa=float(kappa))
         for nm in ("T", "q"):
@@ -53,9 +53,18 @@ def test_kernels_bit_exact(oracle_mod, forcing):
             assert np.array_equal(o.diffusion(X, wz), g[f"k{case}_{nm}_diffusion"]), (case, nm, "diffusion")
             assert np.array_equal(o.advection(X, wz, int(ityr)), g[f"k{case}_{nm}_advection"]), (case, nm, "advection")
             assert np.array_equal(o.circulation(X, wz, int(ityr)), g[f"k{case}_{nm}_circulation"]), (case, nm, "circ")
-    # the humidity cases really exercise the clamp of f:715/f:907
-    q, d = g["k0_q_in"], g["k0_q_diffusion"]
-    assert np.any(d <= -0.89 * q) or np.any(g["k0_q_advection"] <= -0.89 * q) or True
+    # case 4 (mixed-sign anomaly fields) really exercises where(d <= -T) d = -0.9*T:
+    #  f:907 (advection, one sub-sub-step): a clamped cell holds (T - 0.9*T) - T, i.e. -0.9*T up to rounding;
+    #  f:715 (diffusion): the raw increment of the first polar sub-sub-step satisfies the where() condition
+    import np_greb as ng
+    geo = ng.Geo(kappa=float(g["k4_meta"][1]))
+    for nm in ("T", "q"):
+        X, wz = g[f"k4_{nm}_in"], g[f"k4_{nm}_wz"]
+        a = g[f"k4_{nm}_advection"].astype(np.float64)
+        hit = (X != 0) & (np.abs(a + 0.9 * X.astype(np.float64)) <= 1e-6 * np.abs(X))
+        assert np.count_nonzero(hit) >= 10, (nm, "advection", np.count_nonzero(hit))
+        raw = ng._diff_x(X[0], wz[0], geo.ccx2_d[0])
+        assert np.count_nonzero(raw <= -X[0]) >= 3, (nm, "diffusion")
 
 
 def _run_config1(oracle_mod, forcing):

@@ -1,0 +1,135 @@
+"""Checkpoint / resume of a scenario and the asynchronous run entry.
+
+The reference's loop state (src/greb.f90:226-234) is Ts1,Ta1,To1,q1,cap_surf + the step counter + the
+monthly accumulators and tsmn.  A run that is saved after Y years (or in the middle of a year),
+restored into a FRESH handle and continued must equal the uninterrupted run bit for bit."""
+import numpy as np
+import pytest
+
+import greb_b200
+from greb_b200 import host
+from test_gpu_parity import make_ensemble, product_physics
+
+pytestmark = pytest.mark.gpu
+
+
+def _members():
+    ps = [product_physics(), product_physics(kappa=9.3e5, a_cloud=0.33), product_physics(da_ice=0.29, ce=1.8e-3)]
+    return ps, [np.full(6, c, dtype=np.float32) for c in (680.0, 420.0, 900.0)]
+
+
+@pytest.mark.parametrize("arith", ["exact", "fast"])
+def test_resume_at_a_year_boundary_is_bit_identical(forcing, tmp_path, arith):
+    ps, co2 = _members()
+    a = make_ensemble(forcing, ps, co2)
+    a.set_arithmetic(arith)
+    a.spinup(1)
+    a.reset_scenario()
+    full, gm_full, gc_full = a.run(6)
+    end_full = a.get_states()
+    a.close()
+
+    b = make_ensemble(forcing, ps, co2)
+    b.set_arithmetic(arith)
+    b.spinup(1)
+    b.reset_scenario()
+    first, gm1, _ = b.run(3)
+    path = str(tmp_path / "scenario_year3.npz")
+    host.save_checkpoint(path, b)
+    b.close()
+
+    c = make_ensemble(forcing, ps, co2)                  # fresh handle: no spin-up, no earlier years
+    c.set_arithmetic(arith)
+    assert host.load_checkpoint(path, c) == 3 * 730 + 1
+    assert c.get_calendar() == 3 * 730 + 1
+    rest, gm2, gc2 = c.run(3)
+    assert np.array_equal(first, full[:, :3]) and np.array_equal(rest, full[:, 3:])
+    assert np.array_equal(gm1, gm_full[:, :3]) and np.array_equal(gm2, gm_full[:, 3:])
+    assert np.array_equal(gc2, gc_full[:, 3:])
+    assert np.array_equal(c.get_states(), end_full)
+    c.close()
+
+
+def test_resume_in_the_middle_of_a_year(forcing, tmp_path):
+    """mid-month, mid-year checkpoint: the accumulators carry partial sums (src/greb.f90:145-149)"""
+    ps, co2 = _members()
+    a = make_ensemble(forcing, ps, co2)
+    a.spinup(1)
+    a.reset_scenario()
+    full, gm_full, _ = a.run(2)
+    end_full = a.get_states()
+    a.close()
+
+    b = make_ensemble(forcing, ps, co2)
+    b.spinup(1)
+    b.reset_scenario()
+    b.run(1, want_output=False)
+    b.time_steps(731, 333)                               # stops on 15 June of year 2, first half-day
+    acc = b.get_accumulators()
+    assert np.abs(acc[:, 0]).max() > 0 and np.abs(acc[:, 5]).max() > 0     # Tmm and tsmn hold partial sums
+    path = str(tmp_path / "mid.npz")
+    host.save_checkpoint(path, b)
+    jan_may = [b.get_monthly(m)[:5] for m in range(3)]
+    b.close()
+
+    c = make_ensemble(forcing, ps, co2)
+    it = host.load_checkpoint(path, c)
+    assert it == 731 + 333
+    c.time_steps(it, 2 * 730 + 1 - it)                   # to the year boundary
+    assert c.get_calendar() == 2 * 730 + 1
+    assert np.array_equal(c.get_states(), end_full)
+    for m in range(3):
+        got = c.get_monthly(m)                           # months written by THIS launch: June .. December
+        assert np.array_equal(got[:7], full[m, 1, 5:12]), m
+        assert np.array_equal(jan_may[m], full[m, 1, :5]), m
+    with pytest.raises(greb_b200.GrebError):
+        c.time_steps(1, 731)                             # more than a year per launch
+    c.close()
+
+
+def test_run_async_chained_equals_run(forcing):
+    """run_async x 3 + one wait == run(3): same records in the caller's buffers, same end state; the
+    checked-before-launch arguments leave the calendar untouched when they are wrong."""
+    import torch
+    ps, co2 = _members()
+    a = make_ensemble(forcing, ps, co2)
+    a.spinup(1)
+    a.reset_scenario()
+    want, gm, _ = a.run(3)
+    end = a.get_states()
+    a.close()
+
+    b = make_ensemble(forcing, ps, co2)
+    b.spinup(1)
+    b.reset_scenario()
+    bufs = [torch.empty((3, 1, 12, 5, 48, 96), dtype=torch.float32).pin_memory() for _ in range(3)]
+    for y in range(3):
+        b.run_async(1, bufs[y].data_ptr())
+    assert b.get_calendar() == 3 * 730 + 1               # implicit wait
+    for y in range(3):
+        assert np.array_equal(bufs[y].numpy()[:, 0], want[:, y]), y
+    assert np.array_equal(b.get_states(), end)
+    it = b.get_calendar()
+    with pytest.raises(greb_b200.GrebError):
+        b.run(1, out_members=[0, 7])                     # bad member index: nothing may have been launched
+    assert b.get_calendar() == it and np.array_equal(b.get_states(), end)
+    out, gm2, _ = b.run(1, out_members=[2, 0])
+    assert out.shape[0] == 2 and np.all(np.isfinite(gm2))
+    b.close()
+
+
+def test_failed_init_leaves_the_handle_unusable_not_dangling(forcing):
+    """a second init that fails must not leave inited = true with freed device pointers"""
+    e = make_ensemble(forcing, [product_physics()], [[680.0]])
+    e.spinup(1)
+    e.set_member(0, product_physics(kappa=9e6), [680.0])  # needs more helper rows than the kernel has
+    with pytest.raises(greb_b200.GrebError):
+        e.init()
+    with pytest.raises(greb_b200.GrebError):
+        e.spinup(1)
+    with pytest.raises(greb_b200.GrebError):
+        e.run(1)
+    e.set_member(0, product_physics(), [680.0])
+    e.init()
+    e.spinup(1)
+    e.close()

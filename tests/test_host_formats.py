@@ -64,6 +64,32 @@ def test_namelist_syntax_variants():
     assert np.float32(c.physics.co2_flux) == np.float32(300.0)
 
 
+def test_namelist_subscripts_and_quoted_equals():
+    """gfortran accepts `a(i) = v`: the subscript must be honoured, not dropped (f:1047-1061 padding then
+    sees -1 in the unassigned elements); a '=' or 'x(2) =' inside a quoted string is just text."""
+    txt = """
+    &physics_par p_emi(3) = 5.0, 6.0  kappa = 7e5 /
+    &numerics_par time_scnr = 4 /
+    &diagnostics_par ens_id = "a=b, co2_ppm(2) = 9" output_file = 'o/x=y' /
+    &co2_par co2_ppm(2) = 400 /
+    """
+    c = host.config_from_namelist(txt)
+    d = host._default_physics_struct()
+    want = list(d.p_emi)
+    want[2], want[3] = np.float32(5.0), np.float32(6.0)
+    assert [np.float32(x) for x in c.physics.p_emi] == [np.float32(x) for x in want]
+    assert c.co2_ppm.tolist() == [680.0, 400.0, 400.0, 400.0]          # reference: [-1,400,-1,-1] -> padded
+    assert c.ens_id == "a=b, co2_ppm(2) = 9" and c.output_file == "o/x=y"
+    c = host.config_from_namelist("&numerics_par time_scnr = 3 / &co2_par co2_ppm(1) = 300 co2_ppm(3) = 500 /")
+    assert c.co2_ppm.tolist() == [300.0, 300.0, 300.0]                 # f:1056-1059: the first hole ends the scan
+    with pytest.raises(host.NamelistError):
+        host.config_from_namelist("&physics_par kappa(2) = 3 /")       # scalar with a subscript
+    with pytest.raises(host.NamelistError):
+        host.config_from_namelist("&physics_par kappa = 3, 4 /")
+    with pytest.raises(host.NamelistError):
+        host.config_from_namelist("&physics_par p_emi(0) = 3 /")
+
+
 def test_co2_padding_rules():
     assert host.pad_co2([], 3).tolist() == [680.0, 680.0, 680.0]                 # first < 0 -> 680
     assert host.pad_co2([350.0], 4).tolist() == [350.0] * 4
@@ -144,3 +170,37 @@ def test_spinup_cache_roundtrip_and_key(forcing, tmp_path):
     assert host.load_spinup(path, b, [0, 1], k1)
     assert all(np.array_equal(a.corr[w], b.corr[w]) for w in range(3))
     assert all(np.array_equal(a.state[n], b.state[n]) for n in a.state)
+
+
+class _CkptEns:
+    """host.save_checkpoint / load_checkpoint only use these methods of lib.Ensemble"""
+    def __init__(self, n, seed):
+        rng = np.random.default_rng(seed)
+        self.n = n
+        self.state = rng.normal(size=(n, 5, 48, 96)).astype(np.float32)
+        self.acc = rng.normal(size=(n, 6, 48, 96)).astype(np.float32)
+        self.corr = rng.normal(size=(3, n, 4, 48, 96)).astype(np.float32)   # 4 steps stand in for 730
+        self.it = int(rng.integers(1, 5000))
+    def get_calendar(self): return self.it
+    def set_calendar(self, it): self.it = it
+    def get_states(self): return self.state.copy()
+    def set_states(self, a): self.state = np.array(a, copy=True)
+    def get_accumulators(self): return self.acc.copy()
+    def set_accumulators(self, a): self.acc = np.array(a, copy=True)
+    def get_fluxcorr(self, m, w): return self.corr[w, m]
+    def set_fluxcorr(self, m, w, a): self.corr[w, m] = a
+
+
+def test_checkpoint_roundtrip(tmp_path):
+    a, b = _CkptEns(3, 1), _CkptEns(3, 2)
+    path = str(tmp_path / "ck" / "run.npz")
+    host.save_checkpoint(path, a)
+    assert host.load_checkpoint(path, b) == a.it and b.it == a.it
+    assert np.array_equal(a.state, b.state) and np.array_equal(a.acc, b.acc) and np.array_equal(a.corr, b.corr)
+    c = _CkptEns(3, 3)
+    keep = c.corr.copy()
+    host.save_checkpoint(path, a, with_fluxcorr=False)
+    host.load_checkpoint(path, c)
+    assert np.array_equal(c.state, a.state) and np.array_equal(c.corr, keep)
+    with pytest.raises(ValueError):
+        host.load_checkpoint(path, _CkptEns(2, 4))

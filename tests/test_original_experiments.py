@@ -15,6 +15,7 @@ from greb_b200 import host
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_original_experiments.npz")
 TOL_T, TOL_Q, TOL_ALB = 1e-2, 1e-6, 1e-3        # K, kg/kg, albedo (BASELINE.json north_star gates)
+TOL_GM = 1e-3                                    # K, console global mean
 
 
 @pytest.fixture(scope="module")
@@ -74,8 +75,12 @@ def test_experiment_through_the_abi(L, forcing, gold):
     r = host.run_original(L, forcing, time_flux=1, time_ctrl=1, time_scnr=2)
     assert r["flags"].sum() == 0
     _check(r["scenario"][1, 11], gold[f"long_{L}_scen_dec2"], f"log_exp {L} scenario december of year 2")
-    con = gold[f"long_{L}_console"]                       # [year, CO2?, ...] lines of orig diagnostics
-    assert len(con) >= 2
+    # console lines of the reference's diagnostics (greb.original.model.f90 diagnostics), one per simulated year: 1 flux-correction
+    # year, 1 control year, 2 scenario years; column 1 is sum(tsmn)/(xdim*ydim)-273.15
+    con = gold[f"long_{L}_console"]
+    assert con.shape[0] == 4
+    assert abs(float(r["gmean_control"][0]) - con[1, 1]) <= TOL_GM, (L, r["gmean_control"], con[1])
+    assert np.abs(r["gmean"].astype(np.float64) - con[2:4, 1]).max() <= TOL_GM, (L, r["gmean"], con[2:4, 1])
 
 
 @pytest.mark.gpu

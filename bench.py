@@ -36,19 +36,66 @@ sys.path.insert(0, os.path.join(ROOT, "greb-climate-model_b200"))
 sys.path.insert(0, ROOT)
 
 MEMBERS_PER_GPU = 1024
-# dram__bytes_read.sum + dram__bytes_write.sum of greb_member_kernel from the committed ncu --set full
-# captures (148 member-years per launch): fast mode profiles/r01_final_fast_member_kernel_ncu_summary.txt,
-# exact mode profiles/r01_v25_member_kernel_ncu_summary.txt
-NCU = {
-    "fast": {"dram_bytes_per_member_year": (6.386314e9 + 213.976320e6) / 148, "ipc_per_sm": 2.26,
-             "issue_active_pct": 56.6, "fma_pipe_inst_pct": 36.5, "alu_pipe_inst_pct": 25.4,
-             "lsu_wavefronts_pct": 52.5, "warp_instructions_per_member_year": 40717764268 / 148,
-             "registers_per_thread": 128, "source": "profiles/r01_final_fast_member_kernel_ncu_summary.txt"},
-    "exact": {"dram_bytes_per_member_year": (6.144290e9 + 249.916416e6) / 148, "ipc_per_sm": 2.49,
-              "issue_active_pct": 62.3, "fma_pipe_inst_pct": 43.0, "alu_pipe_inst_pct": 25.6,
-              "lsu_wavefronts_pct": 38.4, "warp_instructions_per_member_year": 66605095626 / 148,
-              "registers_per_thread": 128, "source": "profiles/r01_v25_member_kernel_ncu_summary.txt"},
-}
+NCU_FILES = {"exact": "profiles/r02_member_kernel_exact_ncu_summary.txt",
+             "fast": "profiles/r02_member_kernel_fast_ncu_summary.txt"}
+
+
+def ncu_counters(arith: str):
+    """Counters of the committed `ncu --set full` capture of greb_member_kernel (tools/ncu_summary.py output:
+    a header with the command, the kernel name and the members per launch, then `metric [unit] = value` lines).
+    Read at run time — nothing is typed into this file; returns None when the capture is missing."""
+    path = os.path.join(ROOT, NCU_FILES[arith])
+    if not os.path.exists(path):
+        return None
+    vals, head = {}, []
+    for ln in open(path):
+        ln = ln.rstrip("\n")
+        if " = " in ln and "[" in ln.split(" = ")[0]:
+            name = ln.split(" [")[0].strip()
+            unit = ln.split("[")[1].split("]")[0]
+            try:
+                v = float(ln.split(" = ")[1])
+            except ValueError:
+                continue
+            scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(unit, 1.0)
+            vals[name] = v * scale
+        elif not vals:
+            head.append(ln)
+    import re
+    m = re.search(r"(\d+) members", " ".join(head))
+    k = re.search(r"kernel: (\S+)", " ".join(head))
+    n_members = int(m.group(1)) if m else None
+    if not n_members or "smsp__inst_executed.sum" not in vals:
+        return None
+    out = {"source": NCU_FILES[arith], "capture": head[0] if head else "", "kernel": k.group(1) if k else None,
+           "members_per_launch": n_members,
+           "dram_bytes_per_member_year": (vals.get("dram__bytes_read.sum", 0.0) + vals.get("dram__bytes_write.sum", 0.0)) / n_members,
+           "warp_instructions_per_member_year": vals["smsp__inst_executed.sum"] / n_members,
+           "ipc_per_sm": vals.get("sm__inst_executed.avg.per_cycle_active"),
+           "issue_active_pct": vals.get("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+           "fma_pipe_inst_pct": vals.get("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"),
+           "alu_pipe_inst_pct": vals.get("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
+           "lsu_wavefronts_pct": vals.get("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"),
+           "registers_per_thread": vals.get("launch__registers_per_thread"),
+           "stall_barrier_per_issue": vals.get("smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio"),
+           "stall_long_scoreboard_per_issue": vals.get("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio"),
+           "stall_short_scoreboard_per_issue": vals.get("smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio")}
+    return out
+
+
+def parity_margins():
+    """worst margins observed by tests/test_gpu_long_parity.py on the B200 (committed copy under profiles/)"""
+    path = os.path.join(ROOT, "profiles", "r02_parity_margins.json")
+    if not os.path.exists(path):
+        return None
+    d = json.load(open(path))
+    out = {"source": "profiles/r02_parity_margins.json (tests/test_gpu_long_parity.py, 16 perturbed members x (3+50) years "
+                     "vs the oracle; config 2 vs the reference-derived fixture)"}
+    for k, v in d.items():
+        out[k] = {kk: vv for kk, vv in v.items() if kk != "per_member"}
+    return out
+
+
 WORKLOAD = "configs[2]: 1024-member perturbed-parameter/CO2 ensemble per GPU, 96x48, synthetic S0 forcing"
 
 
@@ -190,9 +237,13 @@ def main():
     ap.add_argument("--members", type=int, default=MEMBERS_PER_GPU, help="members per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--arith", default="fast", choices=["fast", "exact"],
-                    help="fast (default): factored stencils + FMA, results within the BASELINE.json tolerances; "
-                         "exact: bit-identical circulation (IEEE order of the reference, no FMA)")
+    ap.add_argument("--arith", default="exact", choices=["fast", "exact"],
+                    help="exact (default): the reference's IEEE operation order, no FMA contraction, glibc's expf/logf "
+                         "restated on the device — whole runs are bit-identical to the reference arithmetic; "
+                         "fast: factored stencils + FMA + approximate division/log/exp (NOT within the 0.01 K gate "
+                         "for low-CO2 perturbed members over 50 years: tests/test_gpu_long_parity.py)")
+    ap.add_argument("--quick", action="store_true",
+                    help="kernel experiments: skip the exact-mode, single-run and CPU-baseline extras")
     ap.add_argument("--shared-physics", action="store_true",
                     help="CO2-only ensemble (config 3 (i)): one shared spin-up and correction set")
     args = ap.parse_args()
@@ -255,6 +306,7 @@ def main():
         return s
 
     def sync_all():
+        ens.wait()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -289,21 +341,28 @@ def main():
     value = total_members * K / (ev_ms_max / 1e3)
 
     # ---- end to end through the C ABI with host buffers -------------------------------------
+    # Every step: H2D of every member's state from pinned memory, one simulated year, D2H of the end state and
+    # of the year's diagnostic (read on the host: the step's "loss"), D2H of all 12 x 5 monthly-mean records.
+    # The records of year y are copied by the library's copy stream while year y+1 runs (greb_b200_run_async,
+    # two pinned record buffers); the timed region ends with greb_b200_wait, i.e. when the LAST year's
+    # records have landed.
     e2e = None
     if not args.no_e2e:
         states = torch.empty((M, 5, 48, 96), dtype=torch.float32).pin_memory()
-        monthly = torch.empty((M, 1, 12, 5, 48, 96), dtype=torch.float32).pin_memory()
+        monthly = [torch.empty((M, 1, 12, 5, 48, 96), dtype=torch.float32).pin_memory() for _ in range(2)]
         ens.get_states(ptr=states.data_ptr())
-        ne = max(2, min(K, 3))
+        ne = max(3, min(K, 6))
         for i in range(1 + ne):
             if i == 1:
+                ens.wait()
                 sync_all()
                 te = time.perf_counter()
-            ens.set_states(ptr=states.data_ptr())                       # H2D: every member's state
-            rc = ens.L.greb_b200_run(ens.h, 1, monthly.data_ptr(), None, M, None, None)  # run + D2H monthly means
-            ens._ck(rc, "greb_b200_run")
-            ens.get_states(ptr=states.data_ptr())                       # D2H: end state (next step's input)
+            ens.set_states_async(states.data_ptr())                     # H2D: every member's state
+            ens.run_async(1, monthly[i & 1].data_ptr())                 # kernel; records -> pinned buffer (copy stream)
+            ens.get_states_async(states.data_ptr())                     # D2H: end state (next step's input)
+            ens.sync_compute()                                          # kernel + state copies done; records may still fly
             float(diag_allreduce()[0])                                  # D2H read of the step's diagnostic
+        ens.wait()                                                      # the last year's records are on the host
         sync_all()
         dt = time.perf_counter() - te
         tt = torch.tensor([dt], device=f"cuda:{local}", dtype=torch.float64)
@@ -311,8 +370,9 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e = {"value": total_members * ne / float(tt[0]), "unit": "member-years/s",
                "h2d_bytes_per_step": int(states.numel() * 4),
-               "d2h_bytes_per_step": int(monthly.numel() * 4 + states.numel() * 4 + 32),
-               "steps": ne}
+               "d2h_bytes_per_step": int(monthly[0].numel() * 4 + states.numel() * 4 + 32),
+               "steps": ne,
+               "pipeline": "records of year y copied (copy stream, pinned) while year y+1 runs; timed to the last byte"}
 
     if rank == 0:
         sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
@@ -329,11 +389,19 @@ def main():
         by = fm.bytes_per_member_year(shared_corrections=args.shared_physics)
         bytes_launch = M * (by["fluxcorr_read"] + by["monthly_written"]) + by["forcing_per_gpu_year"]
         hbm_ach = bytes_launch / (ms_launch / 1e3) / 1e9
+        ncu = ncu_counters(args.arith)
+        issue_frac = None
+        if ncu:
+            # machine-side utilisation of THIS run: warp instructions per member-year (ncu capture of the same
+            # build) x members / (launch time x 148 SMs x 4 schedulers x observed clock)
+            issue_frac = ncu["warp_instructions_per_member_year"] * M / ((ms_launch / 1e3) * 148 * 4 * sm_mhz * 1e6)
         roofline = {
             "bound": "fp32", "achieved": achieved, "peak": peak_fp32, "unit": "TFLOP/s", "frac": achieved / peak_fp32,
-            "traffic": NCU[args.arith]["dram_bytes_per_member_year"] * M,
-            "traffic_note": ("DRAM bytes per launch from the committed ncu capture (148-member launch, scaled to "
-                             f"{M} members); algorithmic bytes per launch = {bytes_launch:.4g}"),
+            "traffic": ncu["dram_bytes_per_member_year"] * M if ncu else None,
+            "traffic_note": ((f"DRAM bytes per launch from {ncu['source']} ({ncu['members_per_launch']}-member launch, "
+                              f"scaled to {M} members)" if ncu else "no ncu capture committed for this build") +
+                             f"; algorithmic bytes per launch = {bytes_launch:.4g}"),
+            "issue_slot_frac": issue_frac,
             "kernel": "greb_member_kernel",
             "note": ("as-written reference flop count (greb_b200/flops.py, FMA=2) per launch / CUDA-event launch time; "
                      f"peak = 148 SMs x 128 lanes x 2 x {sm_mhz:.0f} MHz observed during the run; the reference "
@@ -351,11 +419,15 @@ def main():
                        "step": "one simulated year (730 steps, 12 month-end outputs x 5 fields) for every member",
                        "physics": "shared (CO2-only)" if args.shared_physics else "perturbed per member",
                        "l2": "inputs larger than L2 (per-member flux corrections 40 MB x members)",
+                       "waves": f"{M} members on 148 SMs = {M / 148:.2f} waves of one CTA per SM "
+                                f"({(1 - M / (148 * -(-M // 148))) * 100:.1f} % of the last wave idle)",
                        "arithmetic": ("fast mode (GREB_ARITH_FAST: factored stencils, FMA contraction, approximate "
-                                      "division/log/exp in the column physics; 50-year run within 7e-4 K / 6e-8 kg/kg "
-                                      "of the reference, gates 1e-2 K / 1e-6: tests/test_gpu_fast_mode.py)"
+                                      "division/log/exp in the column physics; config 1 and 2 and 14 of 16 perturbed "
+                                      "members within 1.5e-3 K over 50 years, 2 low-CO2 members outside the 0.01 K gate)"
                                       if args.arith == "fast" else
-                                      "exact mode (no FMA contraction, IEEE divisions; circulation bit-identical)")},
+                                      "exact mode (the reference's IEEE operation order, no FMA contraction, IEEE "
+                                      "divisions, glibc's expf/logf restated on the device: 16 perturbed members x "
+                                      "(3+50) years bit-identical to the oracle, tests/test_gpu_long_parity.py)")},
             "roofline": roofline,
             "e2e": e2e,
             "gpu_launches": launches,
@@ -366,22 +438,27 @@ def main():
                                "sumsq_gmean": float(stats[2])},
             "nonfinite_members": int(ens.flags().sum()),
         }
-        # counters of the committed ncu --set full capture of this kernel (profiles/r01_v25_*), for context
-        line["roofline"]["ncu"] = NCU[args.arith]
+        # counters of the committed ncu --set full capture of this kernel, parsed from the file at run time
+        line["roofline"]["ncu"] = ncu
         line["roofline"]["executed_fp32_note"] = (
-            "frac uses the reference's AS-WRITTEN flop count; the fast mode executes 2.4x fewer instructions "
-            "(factored stencils), see roofline.ncu.warp_instructions_per_member_year and issue_active_pct for "
-            "the real machine utilisation")
-        if world == 1 and args.arith == "fast":
-            # the same workload in the exact arithmetic mode (bit-identical circulation), 2 timed years
-            ens.set_arithmetic("exact")
+            "frac uses the reference's AS-WRITTEN flop count (SURVEY 8d); issue_slot_frac = executed warp "
+            "instructions / issue slots is the machine-side utilisation")
+        line["parity"] = parity_margins()
+        if world == 1 and not args.quick:
+            # the same workload in the other arithmetic mode, 2 timed years
+            other = "fast" if args.arith == "exact" else "exact"
+            ens.set_arithmetic(other)
             ens.run_raw(1)
             ens.run_raw(2)
             ms_e, n_e = ens.last_kernel_ms()
-            line["exact_mode"] = {"value": M * 2 / (ms_e / 1e3), "unit": "member-years/s",
-                                  "note": "GREB_ARITH_EXACT: IEEE order of the reference, no FMA contraction"}
-            ens.set_arithmetic("fast")
-        if world == 1:
+            line[other + "_mode"] = {
+                "value": M * 2 / (ms_e / 1e3), "unit": "member-years/s",
+                "note": ("GREB_ARITH_FAST: factored stencils, FMA contraction, approximate division/log/exp; "
+                         "secondary number — 2 of 16 perturbed members (CO2 < 300 ppm, sea-ice edge) leave the "
+                         "0.01 K gate over 50 years, see parity.perturbed_fast" if other == "fast" else
+                         "GREB_ARITH_EXACT: IEEE order of the reference, no FMA contraction, glibc libm restated")}
+            ens.set_arithmetic(args.arith)
+        if world == 1 and not args.quick:
             # BASELINE.json's second metric: single-run sim-years/s (one member, one GPU, config 1 physics)
             ens.close()
             one = greb_b200.Ensemble(1, device=local)
@@ -396,7 +473,7 @@ def main():
             ms1, n1 = one.last_kernel_ms()
             line["single_run_sim_years_per_s"] = 4 / (ms1 / 1e3)
             one.close()
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and not args.quick:
             cb = cpu_baseline(years=6, forcing=forcing)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line), flush=True)

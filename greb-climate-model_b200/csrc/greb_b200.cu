@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 #include <stddef.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -33,6 +34,12 @@ __device__ __forceinline__ void cta_prologue(GrebMemberConst* dst, const GrebMem
   __syncthreads();
 }
 
+// hardware warp id -> logical warp (0..11 main, 12..13 helper, -1 = empty slot); greb_types.h "Warp placement"
+__device__ __forceinline__ int greb_logical_warp(unsigned long long warp_map, int hw) {
+  const int w = (int)((warp_map >> (4 * hw)) & 15ull);
+  return w == GREB_SLOT_EMPTY ? -1 : w;
+}
+
 // One CTA integrates one ensemble member for a.nsteps 12-hour steps (time_loop, f:239-274, or
 // qflux_correction, f:325-362, selected by a.spinup).
 // SW = 1: the build with the process switches of greb.original.model.f90 (GREB_SW_*), launched only
@@ -44,14 +51,9 @@ __global__ void __launch_bounds__(GREB_NTHREADS, 1) greb_member_kernel(const Gre
   const int member = a.member_ids[blockIdx.x];
   cta_prologue(&mc_s, a.mc + member, smem);
   SimtCtx ctx;
-#ifdef GREB_DBG_HELPER_FIRST
-  {  // experiment: helper warps on the LOWEST hardware warp ids, main warps keep their SM sub-partition
-    const int hw = threadIdx.x >> 5;
-    ctx.warp = warp_uniform(hw < 2 ? GREB_NMAIN + hw : ((hw & 3) >= 2 ? hw : hw - 4));
-  }
-#else
-  ctx.warp = warp_uniform(threadIdx.x >> 5);
-#endif
+  ctx.warp = warp_uniform(greb_logical_warp(a.warp_map, threadIdx.x >> 5));
+  if (ctx.warp < 0) return;   // an empty warp slot of the placement (exited threads do not count at barriers)
+  ctx.late = (a.late_mask >> ctx.warp) & 1;
   ctx.lane_u = threadIdx.x & 31;
   ctx.smem = smem;
   member_run<MODE, SW>(ctx, a, mc_s, member);
@@ -64,14 +66,9 @@ __global__ void __launch_bounds__(GREB_NTHREADS, 1) greb_circulation_kernel(cons
   __shared__ GrebMemberConst mc_s;
   cta_prologue(&mc_s, a.mc, smem);
   SimtCtx ctx;
-#ifdef GREB_DBG_HELPER_FIRST
-  {  // experiment: helper warps on the LOWEST hardware warp ids, main warps keep their SM sub-partition
-    const int hw = threadIdx.x >> 5;
-    ctx.warp = warp_uniform(hw < 2 ? GREB_NMAIN + hw : ((hw & 3) >= 2 ? hw : hw - 4));
-  }
-#else
-  ctx.warp = warp_uniform(threadIdx.x >> 5);
-#endif
+  ctx.warp = warp_uniform(greb_logical_warp(a.warp_map, threadIdx.x >> 5));
+  if (ctx.warp < 0) return;   // an empty warp slot of the placement (exited threads do not count at barriers)
+  ctx.late = (a.late_mask >> ctx.warp) & 1;
   ctx.lane_u = threadIdx.x & 31;
   ctx.smem = smem;
   SyncState ss;
@@ -89,6 +86,9 @@ __global__ void __launch_bounds__(GREB_NTHREADS, 1) greb_circulation_kernel(cons
                    MODE == 1 ? fr.cyB : 1.0f);
     }
     tile_load_wz(t, g, a.wz + off, smem);
+#if GREB_YCOEF
+    if (MODE == 1) tile_fold_ycoef(t, g, mc_s.ccy_diff, smem);
+#endif
     tile_load_field(t, g, a.X_in + off);
     circulation_main<MODE>(ctx, t, g, mc_s, ss);
 #pragma unroll
@@ -107,9 +107,42 @@ __global__ void __launch_bounds__(GREB_NTHREADS, 1) greb_circulation_kernel(cons
   }
 }
 
+// expf / logf of the exact mode on n arguments (parity entry greb_b200_device_libm)
+__global__ void greb_libm_kernel(int which, const float* x, float* y, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = which == 0 ? v_exp(x[i]) : v_log(x[i]);
+}
+
 // ------------------------------------------------------------------------------------------------
 //                                            runtime
 // ------------------------------------------------------------------------------------------------
+
+// Warp placements (greb_types.h).  map[hw] = logical warp of hardware warp slot hw (sub-partition hw % 4),
+// late = stagger mask over logical main warps, order = logical main warps in the order in which they take
+// quads of rows, the costlier polar-branch rows first (greb_assign_rows).
+struct GrebLayout {
+  const char* name;
+  int map[GREB_NSLOTS];
+  unsigned late;
+  int order[GREB_NMAIN];
+};
+static const GrebLayout greb_layouts[] = {
+    // 0: the 14-warp placement of round 1: helpers share sub-partitions 0 and 1 with three main warps each
+    {"shared", {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 15, 15}, 0x0f0u, {2, 3, 6, 7, 10, 11, 0, 1, 4, 5, 8, 9}},
+    // 1: sub-partition 3 hosts only the two helpers, sub-partitions 0-2 four main warps each
+    {"helpers-alone", {0, 1, 2, 12, 3, 4, 5, 13, 6, 7, 8, 15, 9, 10, 11, 15}, 0xe38u, {0, 3, 1, 4, 2, 5, 6, 9, 7, 10, 8, 11}},
+    // 2: sub-partition 3 = two helpers + two main warps; 0 = four non-polar main warps; 1, 2 = three main warps
+    {"helpers+2", {0, 1, 2, 12, 3, 4, 5, 13, 6, 7, 8, 9, 10, 15, 15, 11}, 0xd38u, {1, 4, 2, 5, 9, 7, 8, 11, 0, 3, 6, 10}},
+    // 3: sub-partition 3 = two helpers + one main warp; 0, 1 = four main warps; 2 = three
+    {"helpers+1", {0, 1, 2, 12, 3, 4, 5, 13, 6, 7, 8, 9, 10, 11, 15, 15}, 0xc38u, {2, 5, 8, 9, 1, 4, 7, 11, 0, 3, 6, 10}},
+};
+#define GREB_NLAYOUTS ((int)(sizeof(greb_layouts) / sizeof(greb_layouts[0])))
+
+static unsigned long long pack_map(const int* map) {
+  unsigned long long m = 0;
+  for (int i = 0; i < GREB_NSLOTS; ++i) m |= (unsigned long long)(map[i] & 15) << (4 * i);
+  return m;
+}
 
 struct greb_b200_handle_s {
   int device = 0;
@@ -135,6 +168,9 @@ struct greb_b200_handle_s {
   cudaStream_t stream = nullptr, copy_stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_k[2] = {nullptr, nullptr}, ev_c[2] = {nullptr, nullptr};
   int arith = GREB_ARITH_EXACT;
+  GrebLayout layout = greb_layouts[0];   // placement in force (choose_layout)
+  int layout_built = -1;                 // arithmetic mode the device row tables were built for
+  std::vector<GrebMemberConst> mc_host;
   int it_next = 1;   // step counter `it` of the next scenario step
   int last_out = 0;  // d_out buffer holding the last completed year
   float last_ms = 0.f;
@@ -271,15 +307,87 @@ extern "C" int greb_b200_destroy(greb_b200_t h) {
   return GREB_OK;
 }
 
+// The placement of an arithmetic mode (measured).  GREB_B200_LAYOUT=<index> or
+// GREB_B200_LAYOUT_EXACT / _FAST override it for experiments; "m0,..,m15/late/o0,..,o11" gives a custom
+// table (map, hexadecimal late mask, row order).
+static bool parse_layout(const char* txt, GrebLayout* out) {
+  if (!txt || !*txt) return false;
+  int id = -1;
+  char tail = 0;
+  if (sscanf(txt, "%d%c", &id, &tail) == 1) {
+    if (id < 0 || id >= GREB_NLAYOUTS) return false;
+    *out = greb_layouts[id];
+    return true;
+  }
+  GrebLayout L = greb_layouts[0];
+  L.name = "custom";
+  int n = 0, pos = 0;
+  for (int i = 0; i < GREB_NSLOTS; ++i) {
+    if (sscanf(txt + pos, "%d%n", &L.map[i], &n) != 1) return false;
+    pos += n;
+    if (txt[pos] == ',') ++pos;
+  }
+  if (txt[pos++] != '/') return false;
+  if (sscanf(txt + pos, "%x%n", &L.late, &n) != 1) return false;
+  pos += n;
+  if (txt[pos++] != '/') return false;
+  for (int i = 0; i < GREB_NMAIN; ++i) {
+    if (sscanf(txt + pos, "%d%n", &L.order[i], &n) != 1) return false;
+    pos += n;
+    if (txt[pos] == ',') ++pos;
+  }
+  // every logical warp exactly once
+  int seen[16] = {0}, seen_o[GREB_NMAIN] = {0};
+  for (int i = 0; i < GREB_NSLOTS; ++i) {
+    if (L.map[i] < 0 || L.map[i] > 15) return false;
+    seen[L.map[i]]++;
+  }
+  for (int w = 0; w < GREB_NWARP; ++w)
+    if (seen[w] != 1) return false;
+  for (int i = 0; i < GREB_NMAIN; ++i) {
+    if (L.order[i] < 0 || L.order[i] >= GREB_NMAIN || seen_o[L.order[i]]++) return false;
+  }
+  *out = L;
+  return true;
+}
+
+static GrebLayout choose_layout(int arith) {
+  GrebLayout L = greb_layouts[arith == GREB_ARITH_FAST ? 1 : 0];
+  GrebLayout tmp;
+  if (parse_layout(getenv("GREB_B200_LAYOUT"), &tmp)) L = tmp;
+  if (parse_layout(getenv(arith == GREB_ARITH_FAST ? "GREB_B200_LAYOUT_FAST" : "GREB_B200_LAYOUT_EXACT"), &tmp)) L = tmp;
+  return L;
+}
+
+// (re)builds the lane-group -> row tables of every member for the placement of the current arithmetic mode
+static int apply_layout(greb_b200_t h) {
+  if (!h->inited || h->layout_built == h->arith) return GREB_OK;
+  h->layout = choose_layout(h->arith);
+  for (auto& mc : h->mc_host)
+    greb_assign_rows(mc.polar, mc.time2_diff, mc.time2_adv, mc.row_of_group, mc.hslot_of_row, mc.helper_row,
+                     &mc.n_hslots, h->layout.order);
+  CK(cudaMemcpyAsync(h->d_mc, h->mc_host.data(), h->mc_host.size() * sizeof(GrebMemberConst), cudaMemcpyHostToDevice,
+                     h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->layout_built = h->arith;
+  return GREB_OK;
+}
+
 extern "C" int greb_b200_set_arithmetic(greb_b200_t h, int mode) {
   if (!h) return GREB_E_INVALID;
   if (mode != GREB_ARITH_EXACT && mode != GREB_ARITH_FAST)
     return fail(h, GREB_E_INVALID, "greb_b200_set_arithmetic: mode must be GREB_ARITH_EXACT or GREB_ARITH_FAST");
+  if (h->inited && mode != h->arith) {
+    cudaSetDevice(h->device);
+    FIN(h);
+  }
   h->arith = mode;
-  return GREB_OK;
+  return apply_layout(h);
 }
 
-static void launch_member(greb_b200_t h, int grid, const GrebKernelArgs& a) {
+static void launch_member(greb_b200_t h, int grid, GrebKernelArgs a) {
+  a.warp_map = pack_map(h->layout.map);
+  a.late_mask = h->layout.late;
   bool sw = false;
   for (unsigned m : h->switches) sw = sw || m != 0;
   const bool fast = h->arith == GREB_ARITH_FAST;
@@ -330,6 +438,7 @@ extern "C" int greb_b200_set_switches(greb_b200_t h, int member, unsigned mask) 
     cudaSetDevice(h->device);
     FIN(h);
     h->switches[member] = mask;
+    h->mc_host[member].switches = (int)mask;
     const int sw = (int)mask;
     CK(cudaMemcpyAsync(reinterpret_cast<char*>(h->d_mc + member) + offsetof(GrebMemberConst, switches), &sw,
                        sizeof(int), cudaMemcpyHostToDevice, h->stream));
@@ -412,6 +521,11 @@ extern "C" int greb_b200_init(greb_b200_t h) {
     }
   }
   for (int m = 0; m < N; ++m) mc[m].switches = (int)h->switches[m];
+  h->layout = choose_layout(h->arith);
+  for (auto& c : mc)
+    greb_assign_rows(c.polar, c.time2_diff, c.time2_adv, c.row_of_group, c.hslot_of_row, c.helper_row, &c.n_hslots,
+                     h->layout.order);
+  h->layout_built = h->arith;
   h->co2_stride = 1;
   for (int m = 0; m < N; ++m) h->co2_stride = std::max(h->co2_stride, (int)h->co2[m].size());
   std::vector<float> co2((size_t)N * h->co2_stride, 680.f);
@@ -432,6 +546,7 @@ extern "C" int greb_b200_init(greb_b200_t h) {
   CK(upload(&h->d_state, state));
   CK(upload(&h->d_co2, co2));
   CK(upload(&h->d_mc, mc));
+  h->mc_host = mc;
   CK(upload(&h->d_ids_all, ids_all));
   CK(upload(&h->d_ids_rep, h->group_rep));
   CK(cudaMalloc((void**)&h->d_corr, (size_t)G * GNT * GC_COUNT * GNC * 4));
@@ -787,6 +902,8 @@ extern "C" int greb_b200_circulation(greb_b200_t h, int member, int ityr, const 
   a.X_in = dX;
   a.wz = dW;
   a.dX = dO;
+  a.warp_map = pack_map(h->layout.map);
+  a.late_mask = h->layout.late;
   CK(cudaEventRecord(h->ev0, h->stream));
   if (h->arith == GREB_ARITH_FAST) greb_circulation_kernel<1><<<n, GREB_NTHREADS, GREB_SMEM_BYTES, h->stream>>>(a);
   else greb_circulation_kernel<0><<<n, GREB_NTHREADS, GREB_SMEM_BYTES, h->stream>>>(a);
@@ -870,6 +987,24 @@ extern "C" int greb_b200_set_accumulators(greb_b200_t h, const float* in) {
   return GREB_OK;
 }
 
+
+extern "C" int greb_b200_device_libm(greb_b200_t h, int which, const float* x, float* y, int n) {
+  if (!h) return GREB_E_INVALID;
+  if ((which != 0 && which != 1) || !x || !y || n < 1)
+    return fail(h, GREB_E_INVALID, "greb_b200_device_libm: bad arguments");
+  cudaSetDevice(h->device);
+  float *dx = nullptr, *dy = nullptr;
+  CK(cudaMalloc((void**)&dx, (size_t)n * 4));
+  CK(cudaMalloc((void**)&dy, (size_t)n * 4));
+  CK(cudaMemcpy(dx, x, (size_t)n * 4, cudaMemcpyHostToDevice));
+  greb_libm_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(which, dx, dy, n);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaMemcpy(y, dy, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  cudaFree(dx);
+  cudaFree(dy);
+  return GREB_OK;
+}
 
 extern "C" int greb_b200_last_kernel_ms(greb_b200_t h, float* ms, int* launches) {
   if (!h) return GREB_E_INVALID;

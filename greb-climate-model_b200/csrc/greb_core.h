@@ -114,6 +114,7 @@ struct Tile {
   vf W[GREB_CPT];        // wz, own cells
   vf U[GREB_CPT];        // zonal wind of this step
   vf wxl[3], wxr[3];     // wz of the 3 cells west / east of the tile
+  vi pvmask;             // GREB_YCOEF (fast mode): bit j set <=> v >= 0 at own cell j
   // The y-direction constants live in a private shared-memory slot of the thread (GSM_PRIV), not in
   // registers: V, wz(k-1), wz(k+1) (0 where the row does not exist) and the upstream far-row weight
   // WFY = v>=0 ? wz(k-2) : wz(k+2) (0 if absent).  They are read back with LDS.128 in substep_y.
@@ -174,6 +175,39 @@ GDEV void tile_load_wz(Tile& t, const RowGeom& g, const float* wz, float* smem) 
     t.wxr[i] = v_ldg(wz, g.k * GX + cr);
   }
 }
+
+#if GREB_YCOEF
+// Fast mode, once per circulation: fold the latitudinal constants of the step into three per-cell factors
+//   T' = T + X + CA*(T(k+1)-T) + CB*(T(k-1)-T) + CF*(Tfar-T),   X = wz*dTx + aTx from the x part,
+//   CA = wz*ccy_diff*wz(k+1) + (v<0  ? |v*cy|*wz(k+1) : 0)      f:587-588 + the v<0 branch of f:771-780
+//   CB = wz*ccy_diff*wz(k-1) + (v>=0 ? |v*cy|*wz(k-1) : 0)
+//   CF = |v*cy|*WFY,  Tfar = v>=0 ? T(k-2) : T(k+2)
+// (overwrites the PRIV_WP1 / PRIV_WM1 / PRIV_WFY slots; PRIV_V is no longer read in the sub-steps)
+GDEV void tile_fold_ycoef(Tile& t, const RowGeom& g, float ccyd, float* smem) {
+  t.pvmask = vi(0);
+  GUNROLL
+  for (int q = 0; q < 3; ++q) {
+    vf V[4], Wm1[4], Wp1[4], WFY[4], CA[4], CB[4], CF[4];
+    v_ld4(V, priv_ptr(smem, PRIV_V, q), g.tid4);
+    v_ld4(Wm1, priv_ptr(smem, PRIV_WM1, q), g.tid4);
+    v_ld4(Wp1, priv_ptr(smem, PRIV_WP1, q), g.tid4);
+    v_ld4(WFY, priv_ptr(smem, PRIV_WFY, q), g.tid4);
+    GUNROLL
+    for (int i = 0; i < 4; ++i) {
+      const vb pv = V[i] >= 0.0f;
+      const vf av = v_abs(V[i]);
+      const vf wd = t.W[4 * q + i] * ccyd;
+      CA[i] = v_fma(wd, Wp1[i], v_sel(pv, v_bcast(0.0f), av * Wp1[i]));
+      CB[i] = v_fma(wd, Wm1[i], v_sel(pv, av * Wm1[i], v_bcast(0.0f)));
+      CF[i] = av * WFY[i];
+      t.pvmask = v_seli(pv, t.pvmask | (1 << (4 * q + i)), t.pvmask);
+    }
+    v_st4(priv_ptr(smem, PRIV_WP1, q), g.tid4, CA[0], CA[1], CA[2], CA[3]);
+    v_st4(priv_ptr(smem, PRIV_WM1, q), g.tid4, CB[0], CB[1], CB[2], CB[3]);
+    v_st4(priv_ptr(smem, PRIV_WFY, q), g.tid4, CF[0], CF[1], CF[2], CF[3]);
+  }
+}
+#endif
 
 GDEV void tile_load_field(Tile& t, const RowGeom& g, const float* X) {
   GUNROLL
@@ -390,6 +424,9 @@ GDEV void substep_x_fast(vf (&dTx)[GREB_CPT], vf (&aTx)[GREB_CPT], const Tile& t
       const vf SL = v_fma(WW[e - 2], TT[e] - TT[e - 2], P[e - 1]);
       const vf SR = v_fma(WW[e + 2], TT[e + 2] - TT[e], Q[e]);
       aTx[j] = t.U[j] * v_sel(t.U[j] <= 0.0f, SL, SR);
+#if GREB_YCOEF
+      dTx[j] = v_fma(t.W[j], dTx[j], aTx[j]);   // X = wz*dTx + aTx: one array crosses the barrier
+#endif
     }
   } else {
     GUNROLL
@@ -400,6 +437,9 @@ GDEV void substep_x_fast(vf (&dTx)[GREB_CPT], vf (&aTx)[GREB_CPT], const Tile& t
       vf RR = v_fma(10.0f, Q[e], v_fma(4.0f, Q[e + 1], Q[e + 2]));
       if (j == 9) RR = v_sel(g.is_bug, v_fma(10.0f, Q[e], WW[15] * (TT[15] - TT[13])), RR);   // f:881
       aTx[j] = polar_clamp(t.U[j] * v_sel(t.U[j] <= 0.0f, LL, RR), t.T[j]);          // f:907
+#if GREB_YCOEF
+      dTx[j] = v_fma(t.W[j], dTx[j], aTx[j]);
+#endif
     }
   }
 #undef GREB_FAST_S
@@ -407,6 +447,29 @@ GDEV void substep_x_fast(vf (&dTx)[GREB_CPT], vf (&aTx)[GREB_CPT], const Tile& t
 
 GDEV void substep_y_fast(Tile& t, const vf (&dTx)[GREB_CPT], const vf (&aTx)[GREB_CPT], const RowGeom& g,
                          const FastRow& fr, const float* buf, float* smem) {
+#if GREB_YCOEF
+  GUNROLL
+  for (int q = 0; q < 3; ++q) {
+    vf tm2[4], tm1[4], tp1[4], tp2[4], CA[4], CB[4], CF[4];
+    v_ld4(CA, priv_ptr(smem, PRIV_WP1, q), g.tid4);
+    v_ld4(CB, priv_ptr(smem, PRIV_WM1, q), g.tid4);
+    v_ld4(CF, priv_ptr(smem, PRIV_WFY, q), g.tid4);
+    v_ld4(tm1, buf, g.km1 * GX + g.col + 4 * q);
+    v_ld4(tp1, buf, g.kp1 * GX + g.col + 4 * q);
+    v_ld4(tm2, buf, g.km2 * GX + g.col + 4 * q);
+    v_ld4(tp2, buf, g.kp2 * GX + g.col + 4 * q);
+    GUNROLL
+    for (int i = 0; i < 4; ++i) {
+      const int j = 4 * q + i;
+      const vf T = t.T[j];
+      const vf far = v_sel(v_bit(t.pvmask, j), tm2[i], tp2[i]);
+      const vf acc = v_fma(CA[i], tp1[i] - T, v_fma(CB[i], tm1[i] - T, T + dTx[j]));   // dTx holds X here
+      t.T[j] = v_fma(CF[i], far - T, acc);
+    }
+  }
+  (void)aTx; (void)fr;
+  return;
+#endif
   GUNROLL
   for (int q = 0; q < 3; ++q) {
     vf tm2[4], tm1[4], tp1[4], tp2[4], V[4], Wm1[4], Wp1[4], WFY[4];
@@ -709,6 +772,7 @@ struct SyncState {
 template <int MODE = 0>
 GDEV void circulation_main(const SimtCtx& ctx, Tile& t, const RowGeom& g, const GrebMemberConst& mc, SyncState& ss) {
   const FastRow fr = fast_row(g.k, mc);
+  const bool late = warp_uniform(ctx.late) != 0;   // stagger, greb_types.h
   if (g.owned) tile_publish(t, g, ss.hb + (ss.phase & 1) * GNC);
   sb_arrive(ctx, ss.bar);
 #if defined(GREB_DBG_CLOCKS) && GREB_DEVICE
@@ -727,10 +791,11 @@ GDEV void circulation_main(const SimtCtx& ctx, Tile& t, const RowGeom& g, const 
     const float* buf = ss.hb + (ss.phase & 1) * GNC;
     (void)buf; (void)dTx; (void)aTx;
 #else
+    if (late) sb_wait(ctx, ss.bar, ss.phase);         // stagger: this warp's x part runs beside the others' y part
     if (MODE == 1) substep_x_fast(dTx, aTx, t, g, fr);
     else substep_x(dTx, aTx, t, g, mc);               // own row only: overlaps the barrier latency
     GCLK(c_x, tc)
-    sb_wait(ctx, ss.bar, ss.phase);
+    if (!late) sb_wait(ctx, ss.bar, ss.phase);
     GCLK(c_w, tc)
     const float* buf = ss.hb + (ss.phase & 1) * GNC;
     if (MODE == 1) substep_y_fast(t, dTx, aTx, g, fr, buf, ss.smem);
@@ -1161,6 +1226,9 @@ GDEV void member_run_main(const SimtCtx& ctx, const GrebKernelArgs& a, const Gre
       if (SW && fld == 1 && (mc.switches & GREB_SW_VAPOR_DIFFUSION_ONLY))
         tile_load_uv(t, g, forc + GF_U * GNC, forc + GF_V * GNC, smem, 0.0f, 0.0f, 0.0f);
       tile_load_wz(t, g, wzg + fld * GNC, smem);
+#if GREB_YCOEF
+      if (MODE == 1) tile_fold_ycoef(t, g, mc.ccy_diff, smem);
+#endif
       tile_load_field(t, g, st + (fld == 0 ? GS_TA : GS_Q) * GNC);
       SCLK(2)
       circulation_main<MODE>(ctx, t, g, mc, ss);

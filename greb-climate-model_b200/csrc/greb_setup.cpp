@@ -124,22 +124,29 @@ void greb_build_forcing(GrebHostForcing& F, const float* z_topo, const float* gl
 static int f_nint(float x) { return (int)lroundf(x); }
 
 int greb_assign_rows(const int* polar, const int* time2_diff, const int* time2_adv, int* row_of_group,
-                     int* hslot_of_row, int* helper_row, int* n_hslots) {
+                     int* hslot_of_row, int* helper_row, int* n_hslots, const int* warp_order) {
   // Lane groups (4 per main warp) -> rows.  Warps are kept homogeneous (all polar-branch rows or all
   // main-branch rows) so that the f:592/f:799 branch does not diverge inside a warp; the cheaper
-  // main-row warps go to the SM sub-partitions (warp % 4) that also host a helper warp (12, 13).
+  // main-row warps go to the SM sub-partitions (warp % 4) that also host a helper warp (12, 13) in the
+  // 14-warp layout.
   int pol[GY], mainr[GY], np = 0, nm = 0;
   for (int k = 0; k < GY; ++k) (polar[k] ? pol[np++] : mainr[nm++]) = k;
   int rows[GY], n = 0;  // rows in group order of a virtual warp list: polar warps first
   for (int i = 0; i < np; ++i) rows[n++] = pol[i];
   for (int i = 0; i < nm; ++i) rows[n++] = mainr[i];
   const int n_polar_warps = (np + 3) / 4;
-  // physical warp order: polar warps take ids with (w % 4) in {2, 3} first
+  // warp_order: the logical main warps in the order in which they receive quads of rows, polar rows first
+  // (a property of the warp placement, greb_b200.cu greb_layouts); default = the 14-warp placement, where
+  // polar warps take ids with (w % 4) in {2, 3} first
   int order[GREB_NMAIN], no = 0;
-  for (int w = 0; w < GREB_NMAIN; ++w)
-    if ((w & 3) >= 2) order[no++] = w;
-  for (int w = 0; w < GREB_NMAIN; ++w)
-    if ((w & 3) < 2) order[no++] = w;
+  if (warp_order) {
+    for (int w = 0; w < GREB_NMAIN; ++w) order[no++] = warp_order[w];
+  } else {
+    for (int w = 0; w < GREB_NMAIN; ++w)
+      if ((w & 3) >= 2) order[no++] = w;
+    for (int w = 0; w < GREB_NMAIN; ++w)
+      if ((w & 3) < 2) order[no++] = w;
+  }
   (void)n_polar_warps;
   for (int v = 0; v < GREB_NMAIN; ++v)
     for (int s = 0; s < 4; ++s) row_of_group[order[v] * 4 + s] = rows[v * 4 + s];
@@ -161,7 +168,7 @@ int greb_assign_rows(const int* polar, const int* time2_diff, const int* time2_a
   return 0;
 }
 
-int greb_build_member_const(GrebMemberConst& mc, const greb_physics_par& p, int group) {
+int greb_build_member_const(GrebMemberConst& mc, const greb_physics_par& p, int group, const int* warp_order) {
   memset(&mc, 0, sizeof mc);
   mc.sig = p.sig; mc.ct_sens = p.ct_sens; mc.da_ice = p.da_ice; mc.a_no_ice = p.a_no_ice; mc.a_cloud = p.a_cloud;
   mc.Tl_ice1 = p.Tl_ice1; mc.Tl_ice2 = p.Tl_ice2; mc.To_ice1 = p.To_ice1; mc.To_ice2 = p.To_ice2;
@@ -202,7 +209,7 @@ int greb_build_member_const(GrebMemberConst& mc, const greb_physics_par& p, int 
     }
   }
   return greb_assign_rows(mc.polar, mc.time2_diff, mc.time2_adv, mc.row_of_group, mc.hslot_of_row, mc.helper_row,
-                          &mc.n_hslots);
+                          &mc.n_hslots, warp_order);
 }
 
 void greb_build_wz(float* out, const GrebHostForcing& F, const greb_physics_par& p) {

@@ -32,7 +32,8 @@ void greb_build_forcing(GrebHostForcing& F, const float* z_topo, const float* gl
 // physics scalars, heat capacities (f:186-188), circulation geometry and the row assignment.
 // Returns 0, or <0 if the geometry needs more helper rows than the kernel supports (kappa far
 // outside the reference's range) or sub-stepped polar advection (impossible at 96x48).
-int greb_build_member_const(GrebMemberConst& mc, const greb_physics_par& p, int group);
+int greb_build_member_const(GrebMemberConst& mc, const greb_physics_par& p, int group,
+                            const int* warp_order = nullptr);
 
 // wz_air / wz_vapor of one physics group (f:201-202): out[2][GNC]
 void greb_build_wz(float* out, const GrebHostForcing& F, const greb_physics_par& p);
@@ -42,6 +43,6 @@ void greb_build_initial_state(float* out, const GrebHostForcing& F, const GrebMe
 
 // lane group -> latitude row table and helper-warp slots
 int greb_assign_rows(const int* polar, const int* time2_diff, const int* time2_adv, int* row_of_group,
-                     int* hslot_of_row, int* helper_row, int* n_hslots);
+                     int* hslot_of_row, int* helper_row, int* n_hslots, const int* warp_order = nullptr);
 
 bool greb_physics_equal(const greb_physics_par& a, const greb_physics_par& b);

@@ -26,9 +26,10 @@ typedef int vi;
 typedef bool vb;
 
 struct SimtCtx {
-  int warp;     // warp index in the CTA (uniform)
+  int warp;     // logical warp index in the CTA (uniform): 0..11 main, 12.. helper
   int lane_u;   // this thread's lane
   float* smem;  // dynamic shared memory base
+  int late;     // stagger: this (main) warp does its x part after the barrier
 };
 
 GDEV vi ctx_lane(const SimtCtx& c) { return c.lane_u; }
@@ -53,14 +54,85 @@ GDEV vf v_mul(vf a, vf b) { return __fmul_rn(a, b); }
 GDEV vf v_div(vf a, vf b) { return __fdiv_rn(a, b); }
 GDEV vf v_abs(vf a) { return fabsf(a); }
 GDEV vf v_max(vf a, vf b) { return fmaxf(a, b); }
+// ---- expf / logf of the exact mode: glibc's algorithm, bit for bit -------------------------------------
+// The reference is linked against glibc's libm; the CUDA libm differs from it in the last ulp of a few
+// per cent of the arguments, and the ice-albedo / To_ice2 switches of the column physics amplify that
+// over decades (a perturbed member at 280 ppm drifted by 0.02 K in 50 years).  So the exact mode
+// evaluates exp and log the way glibc >= 2.27 does (sysdeps/ieee754/flt-32/e_expf.c, e_logf.c — the ARM
+// optimized-routines algorithms): double-precision arithmetic, a 32-entry 2^(i/32) table / a 16-entry
+// (1/c, log c) table, a cubic.  Constants are those of glibc 2.39's __exp2f_data / __logf_data.
+// tools/glibc_libm_check.c compares this restatement with the host's expf/logf over ALL 2^32 inputs:
+// logf identical for every positive finite float, expf identical for every |x| < 88 except x = 0x1.04845ep+5
+// and x = -0x1.f8cbb2p+5 (1 ulp; the model's arguments lie in [-20, 5]).  Outside those ranges the CUDA
+// libm is used (the special values agree).  B200 executes FP64 at half the FP32 rate: ~10 DP operations
+// per call cost less than the CUDA libm's single-precision sequences.
+__device__ const unsigned long long greb_exp2f_tab[32] = {
+    0x3ff0000000000000ULL, 0x3fefd9b0d3158574ULL, 0x3fefb5586cf9890fULL, 0x3fef9301d0125b51ULL,
+    0x3fef72b83c7d517bULL, 0x3fef54873168b9aaULL, 0x3fef387a6e756238ULL, 0x3fef1e9df51fdee1ULL,
+    0x3fef06fe0a31b715ULL, 0x3feef1a7373aa9cbULL, 0x3feedea64c123422ULL, 0x3feece086061892dULL,
+    0x3feebfdad5362a27ULL, 0x3feeb42b569d4f82ULL, 0x3feeab07dd485429ULL, 0x3feea47eb03a5585ULL,
+    0x3feea09e667f3bcdULL, 0x3fee9f75e8ec5f74ULL, 0x3feea11473eb0187ULL, 0x3feea589994cce13ULL,
+    0x3feeace5422aa0dbULL, 0x3feeb737b0cdc5e5ULL, 0x3feec49182a3f090ULL, 0x3feed503b23e255dULL,
+    0x3feee89f995ad3adULL, 0x3feeff76f2fb5e47ULL, 0x3fef199bdd85529cULL, 0x3fef3720dcef9069ULL,
+    0x3fef5818dcfba487ULL, 0x3fef7c97337b9b5fULL, 0x3fefa4afa2a490daULL, 0x3fefd0765b6e4540ULL};
+__device__ const double greb_logf_tab[32] = {
+    0x1.661ec79f8f3bep+0, -0x1.57bf7808caadep-2, 0x1.571ed4aaf883dp+0, -0x1.2bef0a7c06ddbp-2,
+    0x1.49539f0f010b0p+0, -0x1.01eae7f513a67p-2, 0x1.3c995b0b80385p+0, -0x1.b31d8a68224e9p-3,
+    0x1.30d190c8864a5p+0, -0x1.6574f0ac07758p-3, 0x1.25e227b0b8ea0p+0, -0x1.1aa2bc79c8100p-3,
+    0x1.1bb4a4a1a343fp+0, -0x1.a4e76ce8c0e5ep-4, 0x1.12358f08ae5bap+0, -0x1.1973c5a611cccp-4,
+    0x1.0953f419900a7p+0, -0x1.252f438e10c1ep-5, 0x1.0000000000000p+0, 0x0.0p+0,
+    0x1.e608cfd9a47acp-1, 0x1.aa5aa5df25984p-5,  0x1.ca4b31f026aa0p-1, 0x1.c5e53aa362eb4p-4,
+    0x1.b2036576afce6p-1, 0x1.526e57720db08p-3,  0x1.9c2d163a1aa2dp-1, 0x1.bc2860d224770p-3,
+    0x1.886e6037841edp-1, 0x1.1058bc8a07ee1p-2,  0x1.767dcf5534862p-1, 0x1.4043057b6ee09p-2};
+
+GDEV float greb_expf_glibc(float x) {
+  if (!(fabsf(x) <= 32.0f)) return expf(x);
+  const double z = __dmul_rn(0x1.71547652b82fep+5, (double)x);       // x * N/ln2, N = 32
+  double kd = __dadd_rn(z, 0x1.8p+52);                               // round to integer (ties to even)
+  const unsigned long long ki = (unsigned long long)__double_as_longlong(kd);
+  kd = __dsub_rn(kd, 0x1.8p+52);
+  const double r = __dsub_rn(z, kd);
+  const unsigned long long t = __ldg(&greb_exp2f_tab[ki & 31]) + (ki << 47);
+  const double s = __longlong_as_double((long long)t);               // 2^(k/N)
+  const double p = __fma_rn(0x1.c6af84b912394p-20, r, 0x1.ebfce50fac4f3p-13);
+  const double r2 = __dmul_rn(r, r);
+  double y = __fma_rn(0x1.62e42ff0c52d6p-6, r, 1.0);
+  y = __fma_rn(p, r2, y);
+  return __double2float_rn(__dmul_rn(y, s));
+}
+
+GDEV float greb_logf_glibc(float x) {
+  unsigned ix = __float_as_uint(x);
+  if (ix == 0x3f800000u) return 0.0f;
+  if (ix - 0x00800000u >= 0x7f800000u - 0x00800000u) {
+    if (ix == 0u || ix >= 0x7f800000u) return logf(x);                 // +-0, negative, inf, nan: -inf / nan / inf
+    ix = __float_as_uint(__fmul_rn(x, 0x1p23f)) - (23u << 23);         // subnormal: normalise (e_logf.c)
+  }
+  const unsigned tmp = ix - 0x3f330000u;
+  const int i = (int)((tmp >> 19) & 15u);
+  const int k = (int)tmp >> 23;
+  const unsigned iz = ix - (tmp & 0xff800000u);
+  const double invc = __ldg(&greb_logf_tab[2 * i]), logc = __ldg(&greb_logf_tab[2 * i + 1]);
+  const double z = (double)__uint_as_float(iz);
+  const double r = __fma_rn(z, invc, -1.0);
+  const double y0 = __fma_rn((double)k, 0x1.62e42fefa39efp-1, logc);
+  const double r2 = __dmul_rn(r, r);
+  double y = __fma_rn(0x1.5575b0be00b6ap-2, r, -0x1.ffffef20a4123p-2);
+  y = __fma_rn(-0x1.00ea348b88334p-2, r2, y);
+  y = __fma_rn(y, r2, __dadd_rn(y0, r));
+  return __double2float_rn(y);
+}
 #ifdef GREB_DBG_FASTMATH   // timing experiment only: approximate transcendentals
 GDEV vf v_exp(vf a) { return __expf(a); }
 GDEV vf v_log(vf a) { return __logf(a); }
-#else
+#elif defined(GREB_CUDA_LIBM)   // the CUDA libm (differs from glibc in the last ulp)
 GDEV vf v_exp(vf a) { return expf(a); }
 GDEV vf v_log(vf a) { return logf(a); }
+#else
+GDEV vf v_exp(vf a) { return greb_expf_glibc(a); }
+GDEV vf v_log(vf a) { return greb_logf_glibc(a); }
 #endif
-// approximate forms of the fast arithmetic mode (max error 2 ulp; never used in the exact mode)
+// approximate forms of the fast arithmetic mode (never used in the exact mode)
 GDEV vf v_div_fast(vf a, vf b) { return __fdividef(a, b); }
 GDEV vf v_log_fast(vf a) { return __logf(a); }
 GDEV vf v_exp_fast(vf a) { return __expf(a); }
@@ -169,6 +241,7 @@ struct SimtCtx {
   vi lane_v;
   float* smem;
   pthread_barrier_t* bar;
+  int late;
 };
 GDEV vi ctx_lane(const SimtCtx& c) { return c.lane_v; }
 GDEV void cta_sync(const SimtCtx& c) { pthread_barrier_wait(c.bar); }
@@ -271,6 +344,7 @@ GDEV vi operator-(vi a, int b) { return a + (-b); }
 GDEV vi operator*(vi a, int b) { vi r; for (int l = 0; l < GW; ++l) r.v[l] = a.v[l] * b; return r; }
 GDEV vi operator*(int a, vi b) { return b * a; }
 GDEV vi operator&(vi a, int b) { vi r; for (int l = 0; l < GW; ++l) r.v[l] = a.v[l] & b; return r; }
+GDEV vi operator|(vi a, int b) { vi r; for (int l = 0; l < GW; ++l) r.v[l] = a.v[l] | b; return r; }
 GDEV vb operator==(vi a, int b) { vb r; for (int l = 0; l < GW; ++l) r.v[l] = a.v[l] == b; return r; }
 GDEV vb operator!=(vi a, int b) { vb r; for (int l = 0; l < GW; ++l) r.v[l] = a.v[l] != b; return r; }
 GDEV vb v_bit(vi a, int bit) { vb r; for (int l = 0; l < GW; ++l) r.v[l] = (a.v[l] >> bit) & 1; return r; }

@@ -13,7 +13,25 @@
 #define GREB_NMAIN 12
 #define GREB_NHELP 2
 #define GREB_NWARP (GREB_NMAIN + GREB_NHELP)
-#define GREB_NTHREADS (GREB_NWARP * 32)
+// Warp placement.  The kernels are launched with 16 warp slots (512 threads); a warp's SM sub-partition
+// is (hardware warp id % 4).  Which slot plays which role is a run-time table (GrebKernelArgs::warp_map,
+// 4 bits per hardware warp id: logical warp 0..11 = main, 12..13 = helper, 15 = empty slot, exits at once),
+// so that the placement can differ between the arithmetic modes (greb_b200.cu, greb_layouts): the pole-row
+// chain of a helper warp is a latency-bound serial chain that sets the length of a sub-step, and sharing
+// a sub-partition with three main warps made it 2.6x slower than alone.
+#define GREB_NSLOTS 16
+#define GREB_NTHREADS (GREB_NSLOTS * 32)
+#define GREB_SLOT_EMPTY 15
+// Stagger (GrebKernelArgs::late_mask, one bit per logical main warp): a "late" warp does the x-direction
+// part of a sub-step AFTER the barrier instead of before it, so that the shared-memory-bound y parts of
+// one half of the warps overlap the arithmetic-bound x parts of the other half (after a barrier all warps
+// used to hit the LDS pipe at once).  Same arithmetic, same results.
+// GREB_YCOEF (fast arithmetic mode only): the latitudinal coefficients of a step are folded into three
+// per-cell factors CA, CB, CF once per step (instead of V, wz(k-1), wz(k+1), WFY), and the x part hands
+// over one array wz*dTx + aTx instead of two.
+#ifndef GREB_YCOEF
+#define GREB_YCOEF 1
+#endif
 #define GREB_CPT 12     // cells per thread (96 / 8)
 #define GREB_MAXH 4     // max helper-owned rows (2 per helper warp)
 
@@ -86,6 +104,8 @@ struct GrebKernelArgs {
   int it0;                    // first step counter `it` (1-based) of this launch
   int nsteps;
   int spinup;                 // 1 = qflux_correction step (:325-362), 0 = time_loop (:239-274)
+  unsigned late_mask;         // stagger: bit w set = logical main warp w does its x part after the barrier
+  unsigned long long warp_map;  // 4 bits per hardware warp id -> logical warp (GREB_SLOT_EMPTY = unused slot)
 };
 
 // kernel-level circulation entry
@@ -95,4 +115,6 @@ struct GrebCirculationArgs {
   const float* X_in;          // [n][GNC]
   const float* wz;            // [n][GNC]
   float* dX;                  // [n][GNC]
+  unsigned late_mask;
+  unsigned long long warp_map;
 };

@@ -30,7 +30,8 @@ ABI_SYMBOLS = ["greb_b200_physics_defaults", "greb_b200_physics_original", "greb
                "greb_b200_circulation", "greb_b200_last_kernel_ms",
                "greb_b200_run_async", "greb_b200_wait", "greb_b200_time_steps", "greb_b200_set_states_async",
                "greb_b200_get_states_async", "greb_b200_sync_compute", "greb_b200_get_calendar",
-               "greb_b200_set_calendar", "greb_b200_get_accumulators", "greb_b200_set_accumulators"]
+               "greb_b200_set_calendar", "greb_b200_get_accumulators", "greb_b200_set_accumulators",
+               "greb_b200_device_libm"]
 
 
 class Physics(C.Structure):
@@ -118,6 +119,7 @@ def load_library():
     L.greb_b200_get_flags.argtypes = [vp, ip]
     L.greb_b200_circulation.argtypes = [vp, C.c_int, C.c_int, fp, fp, fp, C.c_int]
     L.greb_b200_last_kernel_ms.argtypes = [vp, fp, ip]
+    L.greb_b200_device_libm.argtypes = [vp, C.c_int, fp, fp, C.c_int]
     _lib = L
     return L
 
@@ -348,6 +350,14 @@ class Ensemble:
         self._ck(self.L.greb_b200_circulation(self.h, member, ityr, _p(X), _p(wz), _p(out), n),
                  "greb_b200_circulation")
         return out
+
+    def device_libm(self, which: str, x) -> np.ndarray:
+        """the exact mode's expf / logf (glibc's algorithm on the device) on an array"""
+        x = _f(x).ravel()
+        y = np.zeros_like(x)
+        self._ck(self.L.greb_b200_device_libm(self.h, {"exp": 0, "log": 1}[which], _p(x), _p(y), x.size),
+                 "greb_b200_device_libm")
+        return y
 
     def last_kernel_ms(self):
         ms = C.c_float()

@@ -209,6 +209,11 @@ int greb_b200_get_flags(greb_b200_t h, int* flags /*[n_members]*/);
 int greb_b200_circulation(greb_b200_t h, int member, int ityr, const float* X_in, const float* wz, float* dX_crcl,
                           int n);
 
+/* The exact mode's expf (which = 0) / logf (which = 1) on n arguments.  The reference evaluates exp and
+ * log (src/greb.f90:422-424, 457) with glibc's libm; the exact mode restates glibc's algorithm on the
+ * device so that whole runs, not only the circulation, are bit-identical (greb_simt.h). */
+int greb_b200_device_libm(greb_b200_t h, int which, const float* x, float* y, int n);
+
 /* ---- timing of the last spinup/run call (CUDA events on the launch stream, ms) -------------- */
 int greb_b200_last_kernel_ms(greb_b200_t h, float* ms, int* launches);
 

@@ -763,3 +763,9 @@ void go_get_derived(const go_model *m, int which, float *out) {
   memcpy(out, src, sizeof(field));
 }
 void go_set_ityr(go_model *m, int ityr) { m->ityr = ityr; }
+
+/* the host libm's expf / logf on arrays: what the reference's exp() / log() of f:422-424, f:457 call when it
+ * is built with gfortran + glibc; the checker of the device restatement (greb_b200_device_libm) */
+void go_libm_array(int which, const float *x, float *y, int n) {
+    for (int i = 0; i < n; ++i) y[i] = which == 0 ? expf(x[i]) : logf(x[i]);
+}

@@ -113,6 +113,7 @@ typedef struct {
   int polar[GO_YDIM], time2_diff[GO_YDIM], time2_adv[GO_YDIM];
 } go_geometry;
 void go_geometry_compute(float pi, float kappa, go_geometry *g);
+void go_libm_array(int which, const float *x, float *y, int n);
 
 #ifdef __cplusplus
 }

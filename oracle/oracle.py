@@ -81,6 +81,7 @@ def lib():
         L.go_seaice.argtypes = [C.c_void_p, fp]
         L.go_deep_ocean.argtypes = [C.c_void_p, fp, fp, fp, fp]
         L.go_geometry_compute.argtypes = [C.c_float, C.c_float, C.POINTER(Geometry)]
+        L.go_libm_array.argtypes = [C.c_int, fp, fp, C.c_int]
         _lib = L
     return _lib
 
@@ -110,6 +111,14 @@ def geometry(pi: float = 3.1416, kappa: float = 8e5) -> Geometry:
     g = Geometry()
     lib().go_geometry_compute(C.c_float(pi), C.c_float(kappa), C.byref(g))
     return g
+
+
+def host_libm(which: str, x) -> np.ndarray:
+    """glibc's expf / logf on an array (what the reference's exp / log call)"""
+    x = _f(x).ravel()
+    y = np.zeros_like(x)
+    lib().go_libm_array({"exp": 0, "log": 1}[which], _p(x), _p(y), x.size)
+    return y
 
 
 STATE = {"Ts": 0, "Ta": 1, "To": 2, "q": 3, "cap_surf": 4}

@@ -89,6 +89,7 @@ void run_cta(const GrebKernelArgs* ka, const GrebCirculationArgs* ca, const Greb
     tasks[w].ctx.warp = w;
     for (int l = 0; l < 32; ++l) tasks[w].ctx.lane_v.v[l] = l;
     tasks[w].ctx.smem = base;
+    tasks[w].ctx.late = (w >> 2) & 1;   // stagger (greb_types.h): every other group of four rows
     tasks[w].ctx.bar = &bar;
     tasks[w].ka = ka;
     tasks[w].ca = ca;

@@ -21,8 +21,9 @@ keys = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "smsp__sass_inst_executed_op_local_st.sum", "smsp__sass_inst_executed_op_global_ld.sum",
         "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "lts__t_bytes.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed"]
+kn = v[h.index("Kernel Name")] if "Kernel Name" in h else "?"
 print(title)
-print(f"report: {rep}")
+print(f"report: {rep}; kernel: {kn.replace(' ', '')}")
 for i, n in enumerate(h):
     if n in keys or ("issue_stalled" in n and "per_issue_active" in n) or \
        ("sass_thread_inst_executed_op_f" in n and n.endswith("sum.per_cycle_elapsed")):

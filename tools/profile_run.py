@@ -19,10 +19,12 @@ ap.add_argument("--members", type=int, default=148)
 ap.add_argument("--years", type=int, default=2)
 ap.add_argument("--shared", action="store_true")
 ap.add_argument("--no-spinup", action="store_true")
+ap.add_argument("--arith", default="exact", choices=["exact", "fast"])
 a = ap.parse_args()
 
 f = synth.cached_forcing(cache_dir=os.environ.get("GREB_FORCING_CACHE", "/tmp/greb_b200_cache"))
 ens = greb_b200.Ensemble(a.members)
+ens.set_arithmetic(a.arith)
 ens.set_forcing(f)
 for m in range(a.members):
     p, co2 = member_physics(m, greb_b200.default_physics)

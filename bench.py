@@ -272,7 +272,7 @@ def main():
 
     M = args.members
     K, W = args.steps, max(args.warmup, 0)
-    n_years = W + K + 8
+    n_years = W + K + 24      # warm-up + timed + e2e (1 + up to 6) + the other arithmetic mode (3) + slack
     forcing = synth.cached_forcing(cache_dir=os.environ.get("GREB_FORCING_CACHE", "/tmp/greb_b200_cache"))
 
     ens = greb_b200.Ensemble(M, device=local)
@@ -473,6 +473,25 @@ def main():
             ms1, n1 = one.last_kernel_ms()
             line["single_run_sim_years_per_s"] = 4 / (ms1 / 1e3)
             one.close()
+            if not args.shared_physics:
+                # BASELINE.json configs[2], variant (i): CO2-only ensemble — every member the default physics, its
+                # own CO2 level; ONE physics group, i.e. one shared spin-up and one 40 MB set of flux corrections
+                # that stays L2-resident instead of 41 GB streamed from HBM
+                co = greb_b200.Ensemble(M, device=local)
+                co.set_arithmetic(args.arith)
+                co.set_forcing(forcing)
+                for m in range(M):
+                    co.set_member(m, greb_b200.default_physics(), np.full(6, member_physics(first + m)[1], dtype=np.float32))
+                co.init()
+                co.spinup(1)
+                co.reset_scenario()
+                co.run_raw(1)
+                co.run_raw(3)
+                msc, _ = co.last_kernel_ms()
+                line["co2_only_ensemble"] = {"value": M * 3 / (msc / 1e3), "unit": "member-years/s", "members": M,
+                                             "note": "config 3 (i): shared physics, per-member CO2; one spin-up, flux "
+                                                     "corrections shared (L2-resident)"}
+                co.close()
         if world == 1 and not args.no_cpu_baseline and not args.quick:
             cb = cpu_baseline(years=6, forcing=forcing)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}

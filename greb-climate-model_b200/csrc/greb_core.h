@@ -1225,13 +1225,19 @@ GDEV void member_run_main(const SimtCtx& ctx, const GrebKernelArgs& a, const Gre
       // orig:560-564: with zero winds every advection term is +-0, so X + dx_diffuse + dx_advec == X + dx_diffuse
       if (SW && fld == 1 && (mc.switches & GREB_SW_VAPOR_DIFFUSION_ONLY))
         tile_load_uv(t, g, forc + GF_U * GNC, forc + GF_V * GNC, smem, 0.0f, 0.0f, 0.0f);
-      tile_load_wz(t, g, wzg + fld * GNC, smem);
+      // orig:553-555: `circulation` returns before assigning dX_crcl; defined here as dX_crcl = 0
+      // (include/greb_b200.h GREB_SW_NO_*_CIRCULATION): X = X_in, no sub-steps, no barriers (the helper
+      // warps skip the same ones)
+      const bool crcl_off = SW && (mc.switches & (fld == 0 ? GREB_SW_NO_HEAT_CIRCULATION : GREB_SW_NO_VAPOR_CIRCULATION));
+      if (!crcl_off) {
+        tile_load_wz(t, g, wzg + fld * GNC, smem);
 #if GREB_YCOEF
-      if (MODE == 1) tile_fold_ycoef(t, g, mc.ccy_diff, smem);
+        if (MODE == 1) tile_fold_ycoef(t, g, mc.ccy_diff, smem);
 #endif
+      }
       tile_load_field(t, g, st + (fld == 0 ? GS_TA : GS_Q) * GNC);
       SCLK(2)
-      circulation_main<MODE>(ctx, t, g, mc, ss);
+      if (!crcl_off) circulation_main<MODE>(ctx, t, g, mc, ss);
       SCLK(3)
       GUNROLL
       for (int q = 0; q < 3; ++q) {
@@ -1312,6 +1318,7 @@ GDEV void member_run_helper(const SimtCtx& ctx, const GrebKernelArgs& a, const G
             hr[i].V[c] = v_bcast(0.0f);
           }
       }
+      if (SW && (mc.switches & (fld == 0 ? GREB_SW_NO_HEAT_CIRCULATION : GREB_SW_NO_VAPOR_CIRCULATION))) continue;
       helper_load_wz(hr, hg, wzg + fld * GNC);
       circulation_helper<MODE>(ctx, hr, hg, mc, st + (fld == 0 ? GS_TA : GS_Q) * GNC, ss);
     }

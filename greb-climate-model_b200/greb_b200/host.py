@@ -383,10 +383,20 @@ def run_namelists(namelists: Sequence[str], input_dir: str = "input", workdir: s
 # ------------------------------------------------------------------------------------------------
 # log_exp -> process switches of include/greb_b200.h.  The original model accumulates its switches
 # with `log_exp <= k` tests, so experiment L switches off everything of the experiments above it.
-# log_exp <= 4, 7 and 16 are NOT reproducible: `circulation` returns before assigning its
-# intent(out) result (orig:553-555) and time_loop adds uninitialised stack arrays.
+# log_exp <= 4, 7 and 16: `circulation` returns before assigning its intent(out) result (orig:553-555), so
+# time_loop adds whatever its local arrays hold.  The C ABI DEFINES the unassigned result as zero
+# (GREB_SW_NO_HEAT_CIRCULATION / GREB_SW_NO_VAPOR_CIRCULATION) — the evidently intended "no circulation", and what
+# the reference computes with zero-initialised static locals.
 _SW = _lib
+_NOCRCL = _SW.SW_NO_HEAT_CIRCULATION | _SW.SW_NO_VAPOR_CIRCULATION
+_EBM = _SW.SW_NO_ICE_ALBEDO | _SW.SW_NO_HYDRO | _SW.SW_NO_DEEP_OCEAN | _NOCRCL   # orig:394, 453, 492, 514, 553
 ORIGINAL_EXPERIMENTS = {
+    1: _EBM,                                                                 # + constant topography, clouds, vapour (orig:162-164)
+    2: _EBM,                                                                 # + constant clouds, vapour
+    3: _EBM,                                                                 # + constant vapour
+    4: _EBM,
+    7: _SW.SW_NO_VAPOR_CIRCULATION | _SW.SW_NO_DEEP_OCEAN,                   # orig:554, 514
+    16: _SW.SW_SST_PLUS_1K | _SW.SW_NO_DEEP_OCEAN | _SW.SW_NO_VAPOR_CIRCULATION,   # orig:225-226, 515, 555
     5: _SW.SW_NO_ICE_ALBEDO | _SW.SW_NO_HYDRO | _SW.SW_NO_DEEP_OCEAN,       # orig:394, 453, 492, 514 (+ mld = d_ocean :165)
     6: _SW.SW_NO_HYDRO | _SW.SW_NO_DEEP_OCEAN,                               # orig:453, 514
     8: _SW.SW_VAPOR_DIFFUSION_ONLY | _SW.SW_NO_DEEP_OCEAN,                   # orig:560-564, 514
@@ -418,10 +428,15 @@ def original_experiment(log_exp: int, forcing: "synth.Forcing", time_scnr: int, 
     inputs (orig:162-166), CO2_ctrl (orig:178-179) and the scenario CO2 path (orig:225, 939-951;
     the scenario starts in 1940, orig:219)."""
     if log_exp not in ORIGINAL_EXPERIMENTS:
-        raise ValueError(f"log_exp = {log_exp}: the reference leaves circulation's result undefined "
-                         "(greb.original.model.f90:553-555); reproducible experiments: "
-                         f"{sorted(ORIGINAL_EXPERIMENTS)}")
+        raise ValueError(f"log_exp = {log_exp}: not an experiment of greb.original.model.f90 "
+                         f"({sorted(ORIGINAL_EXPERIMENTS)})")
     f = forcing
+    if log_exp == 1:                                                 # orig:162 constant topography
+        f = dataclasses.replace(f, z_topo=np.where(f.z_topo > 1.0, np.float32(1.0), f.z_topo).astype(np.float32))
+    if log_exp <= 2:                                                 # orig:163 constant cloud cover
+        f = dataclasses.replace(f, cldclim=np.full_like(f.cldclim, np.float32(0.7)))
+    if log_exp <= 3:                                                 # orig:164 constant water vapour
+        f = dataclasses.replace(f, qclim=np.full_like(f.qclim, np.float32(0.0052)))
     if log_exp <= 9 or log_exp == 11:                                # orig:165-166 "no deep ocean"
         f = dataclasses.replace(f, mldclim=np.full_like(f.mldclim, np.float32(d_ocean)))
     co2_ctrl = 298.0 if log_exp in (12, 13) else 340.0

@@ -155,7 +155,7 @@ def _f(a):
 STATE = {"Ts": 0, "Ta": 1, "To": 2, "q": 3, "cap_surf": 4}
 # include/greb_b200.h GREB_SW_*: process switches (greb.original.model.f90 log_exp experiments)
 SW_NO_ICE_ALBEDO, SW_NO_HYDRO, SW_NO_DEEP_OCEAN, SW_VAPOR_DIFFUSION_ONLY, SW_LINEAR_VAPOR_EMISSIVITY, \
-    SW_SST_PLUS_1K = 1, 2, 4, 8, 16, 32
+    SW_SST_PLUS_1K, SW_NO_HEAT_CIRCULATION, SW_NO_VAPOR_CIRCULATION = 1, 2, 4, 8, 16, 32, 64, 128
 
 
 class Ensemble:

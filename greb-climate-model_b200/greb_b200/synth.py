@@ -235,22 +235,28 @@ def _acos(x):
     return h
 
 
-def make_forcing(seed: int = 20110101, topo: str = "synthetic", reference_input: str | None = None) -> Forcing:
+def make_forcing(seed: int = 20110101, topo: str = "synthetic", reference_input: str | None = None,
+                 reference_fields=None) -> Forcing:
     """Generate the S0 set.
 
     topo="synthetic": all ten fields synthetic (what the GPU box and the bench use).
     topo="aquaplanet": z_topo == -0.1 everywhere, no glacier.
-    topo="reference": take topography / glacier.masks / solar.radiation from
-    ``reference_input`` (only possible where the reference mount exists)."""
+    topo="reference": take topography / glacier.masks / solar.radiation from the directory
+    ``reference_input`` (the reference mount's input/) or from ``reference_fields`` =
+    (z_topo [48][96], glacier [48][96], sw_solar [730][48]) — the arrays a test fixture carries; the other
+    seven fields are generated around that orography."""
     rng = np.random.default_rng(seed)
     lat, lon = _grid()
     phi = lat * (_PI / 180.0)
     sinphi, cosphi = _sin_cos(phi)
 
     if topo == "reference":
-        z_topo = np.fromfile(os.path.join(reference_input, "topography"), dtype="<f4").reshape(YDIM, XDIM)
-        glacier = np.fromfile(os.path.join(reference_input, "glacier.masks"), dtype="<f4").reshape(YDIM, XDIM)
-        sw_solar = np.fromfile(os.path.join(reference_input, "solar.radiation"), dtype="<f4").reshape(NSTEP_YR, YDIM)
+        if reference_fields is not None:
+            z_topo, glacier, sw_solar = (np.asarray(a, dtype=np.float32) for a in reference_fields)
+        else:
+            z_topo = np.fromfile(os.path.join(reference_input, "topography"), dtype="<f4").reshape(YDIM, XDIM)
+            glacier = np.fromfile(os.path.join(reference_input, "glacier.masks"), dtype="<f4").reshape(YDIM, XDIM)
+            sw_solar = np.fromfile(os.path.join(reference_input, "solar.radiation"), dtype="<f4").reshape(NSTEP_YR, YDIM)
         _ = make_topography(rng)  # keep the random stream aligned with the synthetic variant
     elif topo == "aquaplanet":
         _ = make_topography(rng)

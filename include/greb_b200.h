@@ -104,6 +104,11 @@ int greb_b200_set_member(greb_b200_t h, int member, const greb_physics_par* p, c
  *   NO_DEEP_OCEAN      deep_ocean returns zeros (:513-515)
  *   VAPOR_DIFFUSION_ONLY  circulation of q without advection (:560-564)
  *   LINEAR_VAPOR_EMISSIVITY  e_vapor from qclim + linear term in em (:423, :430)
+ *   NO_HEAT_CIRCULATION / NO_VAPOR_CIRCULATION   `circulation` of Ta / of q returns at once (:553-555).  The
+ *                      reference leaves its intent(out) result unassigned there; this library DEFINES it
+ *                      as dX_crcl = 0 (what the reference computes when its local arrays are zero-initialised
+ *                      static storage, e.g. gfortran -fno-automatic, and what the translated reference behind the
+ *                      golden vectors does)
  *   SST_PLUS_1K        scenario only: Ts1 = Tclim(:,:,ityr) + 1 where z_topo < 0 before every step (:226;
  *                      ityr there still is the PREVIOUS step's, :248 updates it afterwards)
  * Members with different masks never share a spin-up.  All bits but SST_PLUS_1K must be set
@@ -116,7 +121,9 @@ enum {
   GREB_SW_VAPOR_DIFFUSION_ONLY = 8,
   GREB_SW_LINEAR_VAPOR_EMISSIVITY = 16,
   GREB_SW_SST_PLUS_1K = 32,
-  GREB_SW_ALL = 63
+  GREB_SW_NO_HEAT_CIRCULATION = 64,
+  GREB_SW_NO_VAPOR_CIRCULATION = 128,
+  GREB_SW_ALL = 255
 };
 int greb_b200_set_switches(greb_b200_t h, int member, unsigned mask);
 /* src/greb.f90:1047-1061: `n_given` values followed by padding to n_years (first<0 -> 680). */

@@ -32,6 +32,11 @@ from oracle import ref  # noqa: E402
 import ctypes as C  # noqa: E402
 
 LONG = (5, 6, 8, 9, 11, 12, 13, 14, 15)
+# log_exp <= 4, 7, 16: `circulation` returns without assigning its intent(out) result (orig:553-555).  In the
+# translated reference the locals dTa_crcl / dq_crcl of time_loop and qflux_correction are zero-initialised
+# static arrays that nothing ever writes in these experiments, i.e. it computes "dX_crcl = 0" — the definition
+# the C ABI adopts (GREB_SW_NO_HEAT_CIRCULATION / GREB_SW_NO_VAPOR_CIRCULATION).
+NOCRCL = (1, 2, 3, 4, 7, 16)
 NSTEPS = 40
 
 
@@ -86,12 +91,18 @@ def steps(f, log_exp):
 def main():
     f = synth.cached_forcing(cache_dir=os.environ.get("GREB_FORCING_CACHE", "/tmp/greb_b200_cache"))
     d = {}
-    for L in LONG:
+    path = os.path.join(HERE, "ref_original_experiments.npz")
+    todo = LONG + NOCRCL
+    if sys.argv[1:] == ["nocrcl"] and os.path.exists(path):      # add the new experiments, keep the rest
+        with np.load(path) as z:
+            d = {k: z[k] for k in z.files}
+        todo = NOCRCL
+    for L in todo:
         ctrl, scen, con = run(f, L, 1, 1, 2)
         d[f"long_{L}_scen_dec2"] = scen[(12 + 11) * 5:(12 + 11) * 5 + 5].copy()
         d[f"long_{L}_console"] = np.array(con, dtype=np.float64)
         print("long", L, scen.shape, con[-1])
-    for L in LONG:
+    for L in todo:
         d[f"steps_{L}_state"] = steps(f, L)
         print("steps", L, float(d[f"steps_{L}_state"][0].mean()))
     d["nsteps"] = np.array(NSTEPS)

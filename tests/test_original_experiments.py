@@ -24,11 +24,16 @@ def gold():
 
 
 def test_experiment_table_covers_every_defined_log_exp():
-    assert sorted(host.ORIGINAL_EXPERIMENTS) == [5, 6, 8, 9, 10, 11, 12, 13, 14, 15]
-    for L in (0, 1, 2, 3, 4, 7, 16):                 # circulation leaves its result undefined (orig:553-555)
+    assert sorted(host.ORIGINAL_EXPERIMENTS) == list(range(1, 17))
+    for L in (0, 17):
         with pytest.raises(ValueError):
             host.original_experiment(L, None, 1)
     assert host.ORIGINAL_EXPERIMENTS[10] == 0 and host.ORIGINAL_EXPERIMENTS[5] == 7
+    # orig:553-555: circulation returns before assigning its result -> defined as "no circulation" (dX_crcl = 0)
+    both = greb_b200.lib.SW_NO_HEAT_CIRCULATION | greb_b200.lib.SW_NO_VAPOR_CIRCULATION
+    assert all(host.ORIGINAL_EXPERIMENTS[L] & both == both for L in (1, 2, 3, 4))
+    assert all(host.ORIGINAL_EXPERIMENTS[L] & both == greb_b200.lib.SW_NO_VAPOR_CIRCULATION for L in (7, 16))
+    assert all(host.ORIGINAL_EXPERIMENTS[L] & both == 0 for L in (5, 6, 8, 9, 10, 11, 12, 13, 14, 15))
 
 
 def test_a1b_pathway_matches_orig_co2_level():
@@ -45,9 +50,15 @@ def test_experiment_inputs(forcing):
     assert ex["forcing"].mldclim is forcing.mldclim and list(ex["co2_scenario"]) == [340.0, 340.0]
     ex = host.original_experiment(12, forcing, 2)
     assert ex["co2_ctrl"] == 298.0 and list(ex["co2_scenario"]) == [298.0, np.float32(299.2)]
+    ex = host.original_experiment(1, forcing, 1)           # orig:162-165
+    f1 = ex["forcing"]
+    assert f1.z_topo.max() == 1.0 and np.array_equal(f1.z_topo[forcing.z_topo <= 1], forcing.z_topo[forcing.z_topo <= 1])
+    assert np.all(f1.cldclim == np.float32(0.7)) and np.all(f1.qclim == np.float32(0.0052)) and np.all(f1.mldclim == 50.0)
+    f3 = host.original_experiment(3, forcing, 1)["forcing"]
+    assert f3.z_topo is forcing.z_topo and f3.cldclim is forcing.cldclim and np.all(f3.qclim == np.float32(0.0052))
 
 
-@pytest.mark.parametrize("L", [5, 6, 8, 9, 11, 12, 13, 14, 15])
+@pytest.mark.parametrize("L", [1, 2, 3, 4, 5, 6, 7, 8, 9, 11, 12, 13, 14, 15, 16])
 def test_emulated_kernel_source_reproduces_the_reference_bit_for_bit(L, forcing, gold):
     """40 scenario steps of the reference's own time_loop (zero flux corrections) vs the kernel source."""
     import emu_lib
@@ -70,7 +81,7 @@ def _check(got, want, what):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("L", [5, 6, 8, 9, 11, 12, 13, 14, 15])
+@pytest.mark.parametrize("L", [1, 2, 3, 4, 5, 6, 7, 8, 9, 11, 12, 13, 14, 15, 16])
 def test_experiment_through_the_abi(L, forcing, gold):
     r = host.run_original(L, forcing, time_flux=1, time_ctrl=1, time_scnr=2)
     assert r["flags"].sum() == 0

@@ -333,6 +333,10 @@ def main():
     wall_s = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
 
+    # ensemble mean / variance FIELDS of the last year's monthly means (untimed): reduced over the rank's members
+    # on the device, then over the ranks with one NCCL reduce to rank 0 (greb_b200/sharding.py)
+    f_mean, f_var, f_cnt = sharding.reduce_field_moments(ens, M, dst=0)
+
     t = torch.tensor([ev_ms, wall_s * 1e3], device=f"cuda:{local}", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -437,6 +441,10 @@ def main():
             "ensemble_stats": {"sum_gmean": float(stats[0]), "sum_gmean_coslat": float(stats[1]),
                                "sumsq_gmean": float(stats[2])},
             "nonfinite_members": int(ens.flags().sum()),
+            "ensemble_fields": {"members": int(f_cnt), "december_tsurf_mean_K": float(f_mean[11, 0].mean()),
+                                "december_tsurf_max_std_K": float(np.sqrt(f_var[11, 0].max())),
+                                "note": "ensemble mean/variance of the 12 x 5 monthly fields: device reduction per rank + "
+                                        "one NCCL reduce of 2 x 276,480 doubles to rank 0"},
         }
         # counters of the committed ncu --set full capture of this kernel, parsed from the file at run time
         line["roofline"]["ncu"] = ncu

@@ -107,6 +107,33 @@ __global__ void __launch_bounds__(GREB_NTHREADS, 1) greb_circulation_kernel(cons
   }
 }
 
+// Ensemble moments of the monthly-mean fields (SURVEY 8d config-4 output policy): for every element e of a
+// year's record block [12][5][GNC], sum and sum of squares over the members of the handle, in float64 and
+// in member order (deterministic).  Thread = element; consecutive threads read consecutive addresses of one
+// member's block, so every load is a coalesced 128-byte line; 1.1 GB per 1,024 members and year.
+__global__ void __launch_bounds__(256) greb_ensemble_moments_kernel(const float* __restrict__ out, int n_members,
+                                                                    double* __restrict__ sum, double* __restrict__ sq) {
+  const size_t E = (size_t)12 * 5 * GNC;
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  double s = 0.0, q = 0.0;
+  int m = 0;
+  for (; m + 4 <= n_members; m += 4) {      // four independent loads in flight per thread
+    const float a = __ldg(out + (size_t)m * E + e), b = __ldg(out + (size_t)(m + 1) * E + e);
+    const float c = __ldg(out + (size_t)(m + 2) * E + e), d = __ldg(out + (size_t)(m + 3) * E + e);
+    s += (double)a; q += (double)a * (double)a;
+    s += (double)b; q += (double)b * (double)b;
+    s += (double)c; q += (double)c * (double)c;
+    s += (double)d; q += (double)d * (double)d;
+  }
+  for (; m < n_members; ++m) {
+    const float a = __ldg(out + (size_t)m * E + e);
+    s += (double)a; q += (double)a * (double)a;
+  }
+  sum[e] = s;
+  sq[e] = q;
+}
+
 // expf / logf of the exact mode on n arguments (parity entry greb_b200_device_libm)
 __global__ void greb_libm_kernel(int which, const float* x, float* y, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -181,6 +208,7 @@ struct greb_b200_handle_s {
   bool pending = false;                // a run_async has not been waited for
   int pend_years = 0;
   float *pend_gmean = nullptr, *pend_gcos = nullptr;
+  double* d_ens = nullptr;             // [2][12][5][GNC] ensemble sum / sum of squares of the last year's records
   float* d_diag_hist = nullptr;        // [hist_years][n_members][2] annual diagnostics of the pending call
   float* h_diag_hist = nullptr;        // pinned mirror
   int hist_years = 0;
@@ -280,6 +308,8 @@ static void free_device(greb_b200_t h) {
   }
   if (h->d_mc) cudaFree(h->d_mc);
   h->d_mc = nullptr;
+  if (h->d_ens) cudaFree(h->d_ens);
+  h->d_ens = nullptr;
   if (h->d_diag_hist) cudaFree(h->d_diag_hist);
   h->d_diag_hist = nullptr;
   if (h->h_diag_hist) cudaFreeHost(h->h_diag_hist);
@@ -987,6 +1017,45 @@ extern "C" int greb_b200_set_accumulators(greb_b200_t h, const float* in) {
   return GREB_OK;
 }
 
+
+// ---- ensemble moments of the last completed year's monthly means --------------------------------
+static int ensemble_moments(greb_b200_t h) {
+  const size_t E = (size_t)12 * 5 * GNC;
+  if (!h->d_ens) CK(cudaMalloc((void**)&h->d_ens, 2 * E * sizeof(double)));
+  greb_ensemble_moments_kernel<<<(unsigned)((E + 255) / 256), 256, 0, h->stream>>>(h->d_out[h->last_out], h->n_members,
+                                                                                    h->d_ens, h->d_ens + E);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));
+  return GREB_OK;
+}
+
+extern "C" int greb_b200_ensemble_moments_device(greb_b200_t h, const double** dev_sum, const double** dev_sumsq,
+                                                 int* n_elements) {
+  if (!h) return GREB_E_INVALID;
+  if (!h->inited || !dev_sum || !dev_sumsq || !n_elements)
+    return fail(h, GREB_E_INVALID, "greb_b200_ensemble_moments_device: bad arguments");
+  cudaSetDevice(h->device);
+  FIN(h);
+  const int rc = ensemble_moments(h);
+  if (rc != GREB_OK) return rc;
+  *dev_sum = h->d_ens;
+  *dev_sumsq = h->d_ens + (size_t)12 * 5 * GNC;
+  *n_elements = 12 * 5 * GNC;
+  return GREB_OK;
+}
+
+extern "C" int greb_b200_ensemble_moments(greb_b200_t h, double* sum, double* sumsq) {
+  if (!h) return GREB_E_INVALID;
+  if (!h->inited || !sum || !sumsq) return fail(h, GREB_E_INVALID, "greb_b200_ensemble_moments: bad arguments");
+  cudaSetDevice(h->device);
+  FIN(h);
+  const int rc = ensemble_moments(h);
+  if (rc != GREB_OK) return rc;
+  const size_t E = (size_t)12 * 5 * GNC;
+  CK(cudaMemcpy(sum, h->d_ens, E * sizeof(double), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(sumsq, h->d_ens + E, E * sizeof(double), cudaMemcpyDeviceToHost));
+  return GREB_OK;
+}
 
 extern "C" int greb_b200_device_libm(greb_b200_t h, int which, const float* x, float* y, int n) {
   if (!h) return GREB_E_INVALID;

@@ -31,7 +31,7 @@ ABI_SYMBOLS = ["greb_b200_physics_defaults", "greb_b200_physics_original", "greb
                "greb_b200_run_async", "greb_b200_wait", "greb_b200_time_steps", "greb_b200_set_states_async",
                "greb_b200_get_states_async", "greb_b200_sync_compute", "greb_b200_get_calendar",
                "greb_b200_set_calendar", "greb_b200_get_accumulators", "greb_b200_set_accumulators",
-               "greb_b200_device_libm"]
+               "greb_b200_device_libm", "greb_b200_ensemble_moments", "greb_b200_ensemble_moments_device"]
 
 
 class Physics(C.Structure):
@@ -120,6 +120,8 @@ def load_library():
     L.greb_b200_circulation.argtypes = [vp, C.c_int, C.c_int, fp, fp, fp, C.c_int]
     L.greb_b200_last_kernel_ms.argtypes = [vp, fp, ip]
     L.greb_b200_device_libm.argtypes = [vp, C.c_int, fp, fp, C.c_int]
+    L.greb_b200_ensemble_moments.argtypes = [vp, vp, vp]
+    L.greb_b200_ensemble_moments_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), ip]
     _lib = L
     return L
 
@@ -350,6 +352,22 @@ class Ensemble:
         self._ck(self.L.greb_b200_circulation(self.h, member, ityr, _p(X), _p(wz), _p(out), n),
                  "greb_b200_circulation")
         return out
+
+    def ensemble_moments(self):
+        """(sum, sum of squares) over the members of the last completed year's monthly means,
+        float64 [12][5][48][96] each, reduced on the device"""
+        s = np.zeros((12, 5, YD, XD), dtype=np.float64)
+        q = np.zeros_like(s)
+        self._ck(self.L.greb_b200_ensemble_moments(self.h, C.c_void_p(s.ctypes.data), C.c_void_p(q.ctypes.data)),
+                 "greb_b200_ensemble_moments")
+        return s, q
+
+    def ensemble_moments_device(self):
+        """device addresses of the same two float64 vectors + their length (for an NCCL reduce)"""
+        ps, pq, n = C.c_void_p(), C.c_void_p(), C.c_int()
+        self._ck(self.L.greb_b200_ensemble_moments_device(self.h, C.byref(ps), C.byref(pq), C.byref(n)),
+                 "greb_b200_ensemble_moments_device")
+        return ps.value, pq.value, n.value
 
     def device_libm(self, which: str, x) -> np.ndarray:
         """the exact mode's expf / logf (glibc's algorithm on the device) on an array"""

@@ -63,3 +63,45 @@ def ensemble_mean_std(moments) -> Tuple[float, float]:
     mean = s / n
     var = max(ss / n - mean * mean, 0.0)
     return mean, var ** 0.5
+
+
+def reduce_field_moments(ens, n_local: int, dst: int | None = 0, group=None):
+    """Ensemble mean and variance FIELDS of the last completed year's monthly means over all ranks.
+
+    Each rank's library reduces its own members on the device (greb_b200_ensemble_moments_device: float64 sum and
+    sum of squares per element of [12][5][48][96]); the two vectors and the member count are then summed
+    across ranks with ONE NCCL reduce to rank `dst` (dst=None: all-reduce) straight from the library's device
+    buffers — 4.4 MB per rank instead of 1.1 MB per member.  Returns (mean, variance, n_total) as float64
+    arrays on the destination rank(s), (None, None, n) elsewhere."""
+    import torch
+    import torch.distributed as dist
+    ps, pq, n = ens.ensemble_moments_device()
+
+    class _View:
+        def __init__(self, ptr):
+            self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+    dev = torch.device("cuda", torch.cuda.current_device())
+    buf = torch.empty(2 * n + 1, dtype=torch.float64, device=dev)
+    buf[:n] = torch.as_tensor(_View(ps), device=dev)
+    buf[n:2 * n] = torch.as_tensor(_View(pq), device=dev)
+    buf[2 * n] = float(n_local)
+    return finish_field_moments(buf, n, dst, group)
+
+
+def finish_field_moments(buf, n: int, dst: int | None = 0, group=None):
+    """the collective + the mean/variance arithmetic of reduce_field_moments on a [sum | sumsq | count]
+    float64 tensor (any device; gloo on CPU in the tests)"""
+    import torch.distributed as dist
+    mine = True
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        if dst is None:
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+        else:
+            dist.reduce(buf, dst=dst, op=dist.ReduceOp.SUM, group=group)
+            mine = dist.get_rank(group) == dst
+    cnt = float(buf[2 * n])
+    if not mine:
+        return None, None, cnt
+    mean = buf[:n] / cnt
+    var = (buf[n:2 * n] / cnt - mean * mean).clamp_(min=0.0)
+    return mean.cpu().numpy().reshape(12, 5, 48, 96), var.cpu().numpy().reshape(12, 5, 48, 96), cnt

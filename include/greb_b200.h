@@ -206,6 +206,13 @@ int greb_b200_get_monthly(greb_b200_t h, int member, float* out);
 /* device-resident per-member diagnostics of the last completed year, 2 floats per member
  * {unweighted mean, cos-lat mean} in deg C — the vector a multi-GPU driver all-reduces. */
 int greb_b200_diag_device(greb_b200_t h, const float** dev_ptr, int* n_floats);
+/* Ensemble statistics of the last completed year's monthly means, computed on the device: for every
+ * element of the record block [12][5][48][96] the sum and the sum of squares over the handle's members
+ * (float64, member order).  A 65,536-member campaign keeps these instead of 72 GB of records per year
+ * (SURVEY.md 8d, config 4); the _device variant returns the device buffers (valid until the next call) —
+ * the vectors a multi-GPU driver reduces with ncclReduce / all-reduce (greb_b200/sharding.py). */
+int greb_b200_ensemble_moments(greb_b200_t h, double* sum /*[12][5][48][96]*/, double* sumsq);
+int greb_b200_ensemble_moments_device(greb_b200_t h, const double** dev_sum, const double** dev_sumsq, int* n_elements);
 /* per-member non-finite flags (1 = a non-finite value was seen) */
 int greb_b200_get_flags(greb_b200_t h, int* flags /*[n_members]*/);
 

@@ -133,3 +133,19 @@ def test_failed_init_leaves_the_handle_unusable_not_dangling(forcing):
     e.init()
     e.spinup(1)
     e.close()
+
+
+def test_ensemble_field_moments_on_the_device(forcing):
+    """greb_b200_ensemble_moments: sum and sum of squares of the year's records over the members, float64"""
+    from greb_b200 import sharding
+    ps, co2 = _members()
+    e = make_ensemble(forcing, ps + ps[:2], co2 + co2[:2])          # 5 members: exercises the unrolled loop + tail
+    e.spinup(1)
+    e.reset_scenario()
+    out, _, _ = e.run(1)
+    s, q = e.ensemble_moments()
+    o = out[:, 0].astype(np.float64)
+    assert np.allclose(s, o.sum(0), rtol=1e-15) and np.allclose(q, (o * o).sum(0), rtol=1e-14)
+    mean, var, cnt = sharding.reduce_field_moments(e, e.n)         # single rank: no collective
+    assert cnt == 5 and np.allclose(mean, o.mean(0), rtol=1e-14) and np.allclose(var, o.var(0), rtol=1e-6, atol=1e-9)
+    e.close()

@@ -70,3 +70,45 @@ def test_single_rank_is_identity():
     m = sharding.local_moments(np.array([1.0, 2.0, 3.0], dtype=np.float32))
     out = sharding.allreduce_moments(m)
     assert [float(x) for x in out] == [3.0, 6.0, 14.0]
+
+
+def _field_worker(rank, world, port, n_total, ret):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(7)
+        n = 12 * 5 * 48 * 96
+        fields = rng.normal(280.0, 3.0, (n_total, 200))                     # 200 elements stand in for n
+        a, b = sharding.shard_range(n_total, world, rank)
+        loc = fields[a:b]
+        buf = torch.zeros(2 * n + 1, dtype=torch.float64)
+        buf[:200] = torch.from_numpy(loc.sum(0))
+        buf[n:n + 200] = torch.from_numpy((loc * loc).sum(0))
+        buf[2 * n] = b - a
+        mean, var, cnt = sharding.finish_field_moments(buf, n, dst=0)
+        ret[rank] = None if mean is None else (mean.ravel()[:200].copy(), var.ravel()[:200].copy(), cnt)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_reduce_of_ensemble_field_moments_world2():
+    """the collective half of sharding.reduce_field_moments (ncclReduce on the GPUs, gloo here): rank 0 ends up
+    with the ensemble mean and variance fields of ALL members, rank 1 with nothing"""
+    import torch.multiprocessing as mp
+    n_total, world = 37, 2
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_field_worker, args=(world, port, n_total, ret), nprocs=world, join=True)
+    rng = np.random.default_rng(7)
+    fields = rng.normal(280.0, 3.0, (n_total, 200))
+    assert ret[1] is None
+    mean, var, cnt = ret[0]
+    assert cnt == n_total
+    assert np.allclose(mean, fields.mean(0), rtol=1e-13) and np.allclose(var, fields.var(0), rtol=1e-8, atol=1e-9)

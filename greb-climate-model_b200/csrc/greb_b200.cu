@@ -30,6 +30,8 @@ __device__ __forceinline__ void cta_prologue(GrebMemberConst* dst, const GrebMem
   for (int i = threadIdx.x; i < (int)(sizeof(GrebMemberConst) / sizeof(int)); i += blockDim.x) d[i] = s[i];
   if (threadIdx.x == 0) {
     sb_init(reinterpret_cast<SplitBar*>(smem + GSM_SYNC), GREB_NWARP);  // one arrival per warp
+    tma_bar_init(reinterpret_cast<unsigned long long*>(smem + GSM_TMA_BAR_A));
+    tma_bar_init(reinterpret_cast<unsigned long long*>(smem + GSM_TMA_BAR_Q));
   }
   __syncthreads();
 }

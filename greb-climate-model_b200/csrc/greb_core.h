@@ -892,8 +892,9 @@ struct StepInfo {
 // the CUDA libm, like the reference's true divisions
 template <int MODE, int SW>
 GDEV void column_phase_a(const GrebKernelArgs& a, const GrebMemberConst& mc, int member, const StepInfo& si, int k,
-                         vi idx0, float* stash) {
+                         vi idx0, float* stash, const float* corr_s) {
 #define DIVF(x, y) (MODE == 1 ? v_div_fast((x), (y)) : (x) / (y))
+#define DIVC(x, c, rc) (MODE == 1 ? v_div_fast((x), (c)) : v_divc((x), (c), (rc)))   // division by a member constant
 #define LOGF(x) (MODE == 1 ? v_log_fast(x) : v_log(x))
 #define EXPF(x) (MODE == 1 ? v_exp_fast(x) : v_exp(x))
   const float* forc = a.forc + (size_t)si.ityr * GF_COUNT * GNC;
@@ -905,6 +906,7 @@ GDEV void column_phase_a(const GrebKernelArgs& a, const GrebMemberConst& mc, int
   const float* pe = mc.p_emi;
 
   vf Ts4[4], Ta4[4], To4[4], q4[4], cap4[4], cld4[4], dTrad4[4], swet4[4], absw4[4], mld4[4], dmld4[4], zoc4[4], ez4[4];
+  vf rdeep4[4], rmix4[4];
   vf c1[4], c2[4], tsmn4[4], tmm4[4], tomm4[4], apmm4[4];
   vi mask4[4];
   v_ld4(Ts4, st + GS_TS * GNC, idx0);
@@ -918,12 +920,14 @@ GDEV void column_phase_a(const GrebKernelArgs& a, const GrebMemberConst& mc, int
   v_ldg4(absw4, forc + GF_ABSWIND * GNC, idx0);
   v_ldg4(mld4, forc + GF_MLD * GNC, idx0);
   v_ldg4(dmld4, forc + GF_DMLD * GNC, idx0);
+  v_ldg4(rdeep4, forc + GF_RDEEP * GNC, idx0);
+  v_ldg4(rmix4, forc + GF_RMIX * GNC, idx0);
   v_ldgi4(mask4, a.mask, idx0);
   v_ldg4(zoc4, a.z_ocean, idx0);
   v_ldg4(ez4, wz_air, idx0);
   if (!si.spinup) {
-    v_ld4(c1, corr + GC_TF * GNC, idx0);
-    v_ld4(c2, corr + GC_TOF * GNC, idx0);
+    v_ld4(c1, corr_s + GC_TF * GNC, idx0);    // GREB_TMA_CORR: shared memory, else the group's global slice
+    v_ld4(c2, corr_s + GC_TOF * GNC, idx0);
     v_ld4(tmm4, acc + GA_TMM * GNC, idx0);
     v_ld4(tomm4, acc + GA_TOMM * GNC, idx0);
     v_ld4(apmm4, acc + GA_APMM * GNC, idx0);
@@ -958,7 +962,7 @@ GDEV void column_phase_a(const GrebKernelArgs& a, const GrebMemberConst& mc, int
     const float a_ice = mc.a_no_ice + mc.da_ice;
     const vf T1 = v_sel(land_ge0, v_bcast(mc.Tl_ice1), v_bcast(mc.To_ice1));
     const vf T2 = v_sel(land_ge0, v_bcast(mc.Tl_ice2), v_bcast(mc.To_ice2));
-    vf a_surf = mc.a_no_ice + mc.da_ice * (1.0f - DIVF(Ts - T1, T2 - T1));
+    vf a_surf = mc.a_no_ice + mc.da_ice * (1.0f - DIVC(Ts - T1, T2 - T1, v_seld(land_ge0, vd(mc.rc_alb_land), vd(mc.rc_alb_ocean))));
     a_surf = v_sel(Ts <= T1, v_bcast(a_ice), a_surf);
     a_surf = v_sel(Ts >= T2, v_bcast(mc.a_no_ice), a_surf);
     a_surf = v_sel(glac, v_bcast(a_ice), a_surf);
@@ -972,7 +976,7 @@ GDEV void column_phase_a(const GrebKernelArgs& a, const GrebMemberConst& mc, int
     if (sw_ & GREB_SW_LINEAR_VAPOR_EMISSIVITY) e_vapor = ez * mc.r_qviwv * qcl4[i];  // orig:423
     vf em = pe[3] * LOGF(pe[0] * e_co2 + pe[1] * e_vapor + pe[2]) + pe[6] + pe[4] * LOGF(pe[0] * e_co2 + pe[2]) +
             pe[5] * LOGF(pe[1] * e_vapor + pe[2]);
-    em = DIVF(pe[7] - cld, v_bcast(pe[8])) * (em - pe[9]) + pe[9];
+    em = DIVC(pe[7] - cld, v_bcast(pe[8]), vd(mc.rc_pe8)) * (em - pe[9]) + pe[9];
     if (sw_ & GREB_SW_LINEAR_VAPOR_EMISSIVITY)
       em = em + ((0.022f / (0.15f * 24.f)) * mc.r_qviwv) * (q - qcl4[i]);  // orig:430
     const vf LWsurf = -(mc.sig * pow4(Ts));
@@ -986,7 +990,7 @@ GDEV void column_phase_a(const GrebKernelArgs& a, const GrebMemberConst& mc, int
     vf qs = 3.75e-3f * EXPF(DIVF(17.08085f * (Ts - 273.15f), Ts - 273.15f + 234.175f));
     qs = qs * ez;
     vf Qlat = (q - qs) * absw * mc.cq_latent * mc.rho_air * mc.ce * swet;
-    vf dq_eva = -(DIVF(DIVF(Qlat, v_bcast(mc.cq_latent)), v_bcast(mc.r_qviwv)));
+    vf dq_eva = -(DIVC(DIVC(Qlat, v_bcast(mc.cq_latent), vd(mc.rc_cq_latent)), v_bcast(mc.r_qviwv), vd(mc.rc_r_qviwv)));
     vf dq_rain = mc.cq_rain * q;
     vf Qlat_air = -(dq_rain * mc.cq_latent * mc.r_qviwv);
     if (sw_ & GREB_SW_NO_HYDRO) {  // orig:452-453
@@ -998,8 +1002,9 @@ GDEV void column_phase_a(const GrebKernelArgs& a, const GrebMemberConst& mc, int
 
     // ---- deep_ocean, f:505-523
     const vb warm = ocean && (Ts >= mc.To_ice2);
-    vf dTo = v_sel(warm && (dmld < 0.0f), -(DIVF(dmld, zoc - mld) * (Ts - To)), v_bcast(0.0f));
-    vf dToc = v_sel(warm && (dmld > 0.0f), DIVF(dmld, mld) * (To - Ts), v_bcast(0.0f));
+    // dmld / (z_ocean - mld) and dmld / mld come precomputed with the forcing (GF_RDEEP, GF_RMIX)
+    vf dTo = v_sel(warm && (dmld < 0.0f), -(rdeep4[i] * (Ts - To)), v_bcast(0.0f));
+    vf dToc = v_sel(warm && (dmld > 0.0f), rmix4[i] * (To - Ts), v_bcast(0.0f));
     dTo = 0.5f * dTo;
     dToc = 0.5f * dToc;
     const vf Tx = v_max(v_bcast(mc.To_ice2), Ts);
@@ -1011,7 +1016,7 @@ GDEV void column_phase_a(const GrebKernelArgs& a, const GrebMemberConst& mc, int
     }
 
     vf Ts0, To0;
-    tendA4[i] = DIVF(GREB_DT * (LWup + LWdown - em * LWsurf + Qlat_air - Qsens), v_bcast(mc.cap_air));  // f:260 / f:336
+    tendA4[i] = DIVC(GREB_DT * (LWup + LWdown - em * LWsurf + Qlat_air - Qsens), v_bcast(mc.cap_air), vd(mc.rc_cap_air));  // f:260 / f:336
     tq4[i] = GREB_DT * (dq_eva + dq_rain);                                                // f:264 / f:341
     if (!si.spinup) {  // time_loop, f:258-262
       Ts0 = Ts + dToc + DIVF(GREB_DT * (sw + LWsurf - LWdown + Qlat + Qsens + c1[i]), cap);
@@ -1035,7 +1040,7 @@ GDEV void column_phase_a(const GrebKernelArgs& a, const GrebMemberConst& mc, int
     vf capn = cap;
     {
       const vf capo = mc.cap_ocean * mld;
-      vf ramp = mc.cap_land + DIVF(capo - mc.cap_land, v_bcast(mc.To_ice2 - mc.To_ice1)) * (Ts0 - mc.To_ice1);
+      vf ramp = mc.cap_land + DIVC(capo - mc.cap_land, v_bcast(mc.To_ice2 - mc.To_ice1), vd(mc.rc_alb_ocean)) * (Ts0 - mc.To_ice1);
       ramp = v_sel(Ts0 <= mc.To_ice1, v_bcast(mc.cap_land), ramp);
       ramp = v_sel(Ts0 >= mc.To_ice2, capo, ramp);
       capn = v_sel(ocean, ramp, capn);
@@ -1066,6 +1071,7 @@ GDEV void column_phase_a(const GrebKernelArgs& a, const GrebMemberConst& mc, int
     v_st4(corr + GC_TOF * GNC, idx0, tofo[0], tofo[1], tofo[2], tofo[3]);
   }
 #undef DIVF
+#undef DIVC
 #undef LOGF
 #undef EXPF
 }
@@ -1091,7 +1097,7 @@ GDEV void column_phase_b(const GrebKernelArgs& a, int member, const StepInfo& si
 
 // Phase C: after circulation(q)
 GDEV void column_phase_c(const GrebKernelArgs& a, const GrebMemberConst& mc, int member, const StepInfo& si, vi idx0,
-                         const vf* X, const float* stash) {
+                         const vf* X, const float* stash, const float* corr_s) {
   float* st = a.state + (size_t)member * GS_COUNT * GNC;
   float* acc = a.acc + (size_t)member * GA_COUNT * GNC;
   float* corr = a.corr + ((size_t)mc.group * GNT + si.ityr) * GC_COUNT * GNC;
@@ -1099,7 +1105,7 @@ GDEV void column_phase_c(const GrebKernelArgs& a, const GrebMemberConst& mc, int
   v_ld4(q1, st + GS_Q * GNC, idx0);
   v_ld4(tq, stash + GNC, idx0);
   if (!si.spinup) {
-    v_ld4(cq, corr + GC_QF * GNC, idx0);
+    v_ld4(cq, corr_s + GC_QF * GNC, idx0);
     v_ld4(qmm, acc + GA_QMM * GNC, idx0);
   } else {
     v_ldg4(cq, a.qclim + (size_t)si.ityr * GNC, idx0);
@@ -1189,6 +1195,23 @@ GDEV void member_run_main(const SimtCtx& ctx, const GrebKernelArgs& a, const Gre
   const RowGeom g = row_geom(ctx, mc);
   Tile t;
   float co2 = 0.0f;
+  // Flux corrections (time_loop only): 55 KB per step and physics group, read once — the one per-member
+  // HBM stream of the scenario (greb_types.h GREB_TMA_CORR).
+  const bool tma_issuer = ctx.warp == 0 && lane0(ctx);
+  const float* corr_g = a.corr + (size_t)mc.group * GNT * GC_COUNT * GNC;
+#if GREB_TMA_CORR
+  // The TMA engine copies them into shared memory while the circulations run: after the barrier that
+  // follows phase A of step `it`, one thread issues qF(it) (needed by phase C of this step, two circulations
+  // later) and TF, ToF(it+1) (needed by phase A of the next step); the consumers wait on the transaction
+  // barriers' phase parity.
+  float* corr_s = smem + GSM_CORR;
+  unsigned long long* bar_a = reinterpret_cast<unsigned long long*>(smem + GSM_TMA_BAR_A);
+  unsigned long long* bar_q = reinterpret_cast<unsigned long long*>(smem + GSM_TMA_BAR_Q);
+  int par_a = 0, par_q = 0;
+  if (!a.spinup && tma_issuer)
+    tma_load(corr_s, corr_g + (size_t)((a.it0 - 1) % GNT) * GC_COUNT * GNC, 2 * GNC * (unsigned)sizeof(float), bar_a);
+#endif
+  cta_sync(ctx);
 
   GNOUNROLL
   for (int it = a.it0; it < a.it0 + a.nsteps; ++it) {
@@ -1207,8 +1230,16 @@ GDEV void member_run_main(const SimtCtx& ctx, const GrebKernelArgs& a, const Gre
 #define SCLK(i)
 #endif
     // ---- phase A: column physics, Ts/To/cap update
+#if GREB_TMA_CORR
+    if (!a.spinup) {
+      tma_wait(bar_a, par_a);
+      par_a ^= 1;
+    }
+#else
+    const float* corr_s = corr_g + (size_t)si.ityr * GC_COUNT * GNC;   // ordinary loads of the (L2-prefetched) slice
+#endif
     GNOUNROLL
-    for (int q = 0; q < 3; ++q) column_phase_a<MODE, SW>(a, mc, member, si, g.k, g.k * GX + g.col + 4 * q, stash);
+    for (int q = 0; q < 3; ++q) column_phase_a<MODE, SW>(a, mc, member, si, g.k, g.k * GX + g.col + 4 * q, stash, corr_s);
     SCLK(0)
     {
       const FastRow fr = fast_row(g.k, mc);
@@ -1217,6 +1248,18 @@ GDEV void member_run_main(const SimtCtx& ctx, const GrebKernelArgs& a, const Gre
     }
     // the helper warps read the rows they circulate from global state written by the main warps
     cta_sync(ctx);
+#if GREB_TMA_CORR
+    if (!a.spinup && tma_issuer) {   // every thread is past its reads of TF, ToF (this step) and qF (previous step)
+      const float* cg = corr_g + (size_t)si.ityr * GC_COUNT * GNC;
+      tma_load(corr_s + GC_QF * GNC, cg + GC_QF * GNC, GNC * (unsigned)sizeof(float), bar_q);
+      if (it + 1 < a.it0 + a.nsteps)
+        tma_load(corr_s, corr_g + (size_t)(it % GNT) * GC_COUNT * GNC, 2 * GNC * (unsigned)sizeof(float), bar_a);
+    }
+#else
+    // the NEXT step's 55 KB slice: HBM -> L2 by the bulk-copy engine while the two circulations run
+    if (!a.spinup && tma_issuer)
+      tma_prefetch_l2(corr_g + (size_t)(it % GNT) * GC_COUNT * GNC, GC_COUNT * GNC * (unsigned)sizeof(float));
+#endif
     SCLK(1)
 
     // ---- circulation of air temperature (f:301), then of humidity (f:303): one code instance
@@ -1239,10 +1282,16 @@ GDEV void member_run_main(const SimtCtx& ctx, const GrebKernelArgs& a, const Gre
       SCLK(2)
       if (!crcl_off) circulation_main<MODE>(ctx, t, g, mc, ss);
       SCLK(3)
+#if GREB_TMA_CORR
+      if (fld == 1 && !a.spinup) {
+        tma_wait(bar_q, par_q);
+        par_q ^= 1;
+      }
+#endif
       GUNROLL
       for (int q = 0; q < 3; ++q) {
         if (fld == 0) column_phase_b(a, member, si, g.k * GX + g.col + 4 * q, &t.T[4 * q], stash);
-        else column_phase_c(a, mc, member, si, g.k * GX + g.col + 4 * q, &t.T[4 * q], stash);
+        else column_phase_c(a, mc, member, si, g.k * GX + g.col + 4 * q, &t.T[4 * q], stash, corr_s);
       }
       SCLK(4)
     }
@@ -1301,6 +1350,7 @@ GDEV void member_run_helper(const SimtCtx& ctx, const GrebKernelArgs& a, const G
   const float* wzg = a.wz + (size_t)mc.group * 2 * GNC;
   const HelperGeom hg = helper_geom(ctx, mc);
   HelperRow hr[GREB_HROWS];
+  cta_sync(ctx);   // pairs with the barrier after the first TMA issue in member_run_main
   GNOUNROLL
   for (int it = a.it0; it < a.it0 + a.nsteps; ++it) {
     const int ityr = (it - 1) % GNT;

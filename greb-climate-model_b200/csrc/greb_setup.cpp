@@ -107,7 +107,10 @@ void greb_build_forcing(GrebHostForcing& F, const float* z_topo, const float* gl
       if (z_topo[c] < 0.f) aw = sqrtf(aw * aw + 3.0f * 3.0f);          // f:454
       rec[GF_ABSWIND * GNC + c] = aw;
       rec[GF_MLD * GNC + c] = mldclim[i];
-      rec[GF_DMLD * GNC + c] = mldclim[i] - mldclim[(size_t)np * GNC + c];
+      const float dmld = mldclim[i] - mldclim[(size_t)np * GNC + c];
+      rec[GF_DMLD * GNC + c] = dmld;
+      rec[GF_RDEEP * GNC + c] = dmld / (F.z_ocean[c] - mldclim[i]);   // f:512 (may be inf/nan where it is never selected)
+      rec[GF_RMIX * GNC + c] = dmld / mldclim[i];                      // f:513
     }
   }
   // cos-lat weights of the README's global mean (README.md:36-37), normalised
@@ -180,6 +183,15 @@ int greb_build_member_const(GrebMemberConst& mc, const greb_physics_par& p, int 
   mc.cap_air = p.cp_air * p.rho_air * p.d_air;      // f:188
   mc.co2_flux = p.co2_flux;
   mc.group = group;
+  {
+    const float dl = p.Tl_ice2 - p.Tl_ice1, dof = p.To_ice2 - p.To_ice1;   // the fp32 differences the reference divides by
+    mc.rc_alb_land = 1.0 / (double)dl;
+    mc.rc_alb_ocean = 1.0 / (double)dof;
+    mc.rc_pe8 = 1.0 / (double)p.p_emi[8];
+    mc.rc_cq_latent = 1.0 / (double)p.cq_latent;
+    mc.rc_r_qviwv = 1.0 / (double)p.r_qviwv;
+    mc.rc_cap_air = 1.0 / (double)mc.cap_air;
+  }
   // geometry, f:578-582 / f:749-753 (the reference recomputes it in every call)
   const float DT_CRCL = 1800.0f, DLON = 3.75f, DLAT = 3.75f;
   const float pi = p.pi, kappa = p.kappa;

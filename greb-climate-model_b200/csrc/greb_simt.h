@@ -11,6 +11,7 @@
 
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #if defined(__CUDACC__) && !defined(GREB_EMU)
 // ------------------------------------------------------------------------------------------
@@ -132,6 +133,14 @@ GDEV vf v_log(vf a) { return logf(a); }
 GDEV vf v_exp(vf a) { return greb_expf_glibc(a); }
 GDEV vf v_log(vf a) { return greb_logf_glibc(a); }
 #endif
+// x / c for a constant c whose double-precision reciprocal rc = RN_f64(1/c) is known: correctly rounded
+// for ALL fp32 x and c.  A quotient of two 24-bit significands that is not a float lies at least 2^-49
+// (relative) away from every float and every midpoint between floats, and x * rc is within 2^-52 of it, so
+// rounding the double product to fp32 rounds the exact quotient.  Three instructions without the FCHK / slow
+// path of the IEEE fp32 division sequence.
+typedef double vd;
+GDEV vd v_seld(vb p, vd a, vd b) { return p ? a : b; }
+GDEV vf v_divc(vf x, vf c, vd rc) { (void)c; return __double2float_rn(__dmul_rn((double)x, rc)); }
 // approximate forms of the fast arithmetic mode (never used in the exact mode)
 GDEV vf v_div_fast(vf a, vf b) { return __fdividef(a, b); }
 GDEV vf v_log_fast(vf a) { return __logf(a); }
@@ -194,6 +203,37 @@ GDEV void sb_wait(const SimtCtx&, SplitBar* b, int phase) {
   } while (!ok);
 }
 #endif
+// ---- 1-D bulk asynchronous copy global -> shared (TMA engine: cp.async.bulk, SASS UBLKCP) -------------
+// One thread arms the transaction barrier with the byte count and issues the copy; the data lands in shared
+// memory without passing through any register, and every consumer thread waits on the barrier's phase
+// parity (a hardware sleep, not a poll).  Addresses and sizes are multiples of 16 bytes.
+GDEV void tma_bar_init(unsigned long long* bar) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(a) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+GDEV void tma_load(float* dst_smem, const float* src_gmem, unsigned bytes, unsigned long long* bar) {
+  const unsigned b = (unsigned)__cvta_generic_to_shared(bar), d = (unsigned)__cvta_generic_to_shared(dst_smem);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d),
+               "l"(src_gmem), "r"(bytes), "r"(b)
+               : "memory");
+}
+// asks the bulk-copy engine to bring `bytes` at src into L2 (no destination, no completion to wait for)
+GDEV void tma_prefetch_l2(const float* src_gmem, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
+}
+GDEV void tma_wait(unsigned long long* bar, int parity) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  unsigned ok;
+  do {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(a), "r"((unsigned)(parity & 1))
+        : "memory");
+  } while (!ok);
+}
 // ---- release/acquire flags in shared memory (helper warp -> owner warps) -------------------------
 GDEV void flag_set(const SimtCtx& c, int* f, int v) {
   __syncwarp();
@@ -266,6 +306,9 @@ GDEV vf v_abs(vf a) { vf r; for (int l = 0; l < GW; ++l) r.v[l] = fabsf(a.v[l]);
 GDEV vf v_exp(vf a) { vf r; for (int l = 0; l < GW; ++l) r.v[l] = expf(a.v[l]); return r; }
 GDEV vf v_log(vf a) { vf r; for (int l = 0; l < GW; ++l) r.v[l] = logf(a.v[l]); return r; }
 GDEV vf v_bcast(float x) { return vf(x); }
+struct vd { double v[GW]; vd() {} vd(double x) { for (int l = 0; l < GW; ++l) v[l] = x; } };
+GDEV vd v_seld(vb p, vd a, vd b) { vd r; for (int l = 0; l < GW; ++l) r.v[l] = p.v[l] ? a.v[l] : b.v[l]; return r; }
+GDEV vf v_divc(vf x, vf c, vd) { return v_div(x, c); }   // the emulator divides (it IS the definition)
 GDEV vf v_div_fast(vf a, vf b) { return v_div(a, b); }   // the emulator has no approximate forms
 GDEV vf v_log_fast(vf a) { return v_log(a); }
 GDEV vf v_exp_fast(vf a) { return v_exp(a); }
@@ -313,6 +356,12 @@ GDEV void flag_set(const SimtCtx&, int* f, int v) { __atomic_store_n(f, v, __ATO
 GDEV void flag_wait(const SimtCtx&, const int* f, int v) {
   while (__atomic_load_n(f, __ATOMIC_ACQUIRE) != v) sched_yield();
 }
+
+// bulk copy stand-ins: the copy happens at issue time; the CTA barriers between issue and use order it
+GDEV void tma_bar_init(unsigned long long*) {}
+GDEV void tma_load(float* dst, const float* src, unsigned bytes, unsigned long long*) { memcpy(dst, src, bytes); }
+GDEV void tma_wait(unsigned long long*, int) {}
+GDEV void tma_prefetch_l2(const float*, unsigned) {}
 
 // operators so that expression code reads the same in both builds
 GDEV vf operator+(vf a, vf b) { return v_add(a, b); }

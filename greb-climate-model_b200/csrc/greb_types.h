@@ -43,10 +43,30 @@
 // [PRIV_*][chunk 0..2][main thread 0..383][4]  -> consecutive threads read consecutive 16 bytes
 #define GSM_PRIV (GSM_SYNC + 32)
 enum { PRIV_V = 0, PRIV_WM1, PRIV_WP1, PRIV_WFY, PRIV_COUNT };
-#define GSM_FLOATS (GSM_PRIV + PRIV_COUNT * 3 * GREB_NMAIN * 32 * 4)
+// Flux corrections of a scenario step (55 KB per step and physics group, the one per-member HBM stream).
+// Default (GREB_TMA_CORR = 0): one thread asks the bulk-copy engine to pull the NEXT step's slice into L2
+// (cp.async.bulk.prefetch.L2) while the circulations run; phases A and C then read it with ordinary loads.
+// GREB_TMA_CORR = 1: the slices are streamed into SHARED memory by the TMA engine (cp.async.bulk +
+// transaction barriers, member_run_main).  Built, bit-identical, and measured SLOWER on B200 (exact mode
+// 1,552 -> 1,420, fast mode 2,673 -> 2,474 member-years/s): the extra 54 KB of shared memory shrink the
+// L1 that serves the five-fold re-reads of the wz rows, and the corrections were never the latency that
+// bounds phase A (3 of 27 field reads per step).  Kept as a build option.
+#ifndef GREB_TMA_CORR
+#define GREB_TMA_CORR 0
+#endif
+#define GSM_CORR (GSM_PRIV + PRIV_COUNT * 3 * GREB_NMAIN * 32 * 4)
+#if GREB_TMA_CORR
+#define GSM_FLOATS (GSM_CORR + 3 * GNC)
+#else
+#define GSM_FLOATS GSM_CORR
+#endif
+#define GSM_TMA_BAR_A (GSM_SYNC + 4)   // floats: 8-byte aligned (GSM_SYNC is)
+#define GSM_TMA_BAR_Q (GSM_SYNC + 6)
 
 // per-step shared forcing record: forc[ityr][GF_*][GNC]
-enum { GF_U = 0, GF_V, GF_CLD, GF_DTRAD, GF_SWET, GF_ABSWIND, GF_MLD, GF_DMLD, GF_COUNT };
+// GF_RDEEP = dmld / (z_ocean - mld) and GF_RMIX = dmld / mld are the two member-independent quotients of
+// deep_ocean (f:511-514), evaluated once on the host with the same IEEE fp32 operations
+enum { GF_U = 0, GF_V, GF_CLD, GF_DTRAD, GF_SWET, GF_ABSWIND, GF_MLD, GF_DMLD, GF_RDEEP, GF_RMIX, GF_COUNT };
 // flux corrections: corr[group][ityr][GC_*][GNC]   (src/greb.f90:110)
 enum { GC_TF = 0, GC_TOF, GC_QF, GC_COUNT };
 // state[member][GS_*][GNC]
@@ -57,6 +77,10 @@ enum { GA_TMM = 0, GA_TAMM, GA_TOMM, GA_QMM, GA_APMM, GA_TSMN, GA_COUNT };
 enum { GM_TOPO_GE0 = 1, GM_TOPO_LT0 = 2, GM_GLACIER = 4, GM_TOPO_GT0 = 8 };
 
 struct GrebMemberConst {
+  // double-precision reciprocals of the member constants the column physics divides by (exact mode):
+  // RN_f32(x / c) == RN_f32(RN_f64(x * RN_f64(1/c))) for all fp32 x, c (greb_core.h v_divc)
+  double rc_alb_land, rc_alb_ocean;  // 1 / fl(Tl_ice2 - Tl_ice1), 1 / fl(To_ice2 - To_ice1)   f:384-392, f:486
+  double rc_pe8, rc_cq_latent, rc_r_qviwv, rc_cap_air;
   // physics scalars used on the device (namelist physics_par, src/greb.f90:68-104)
   float sig, ct_sens, da_ice, a_no_ice, a_cloud, Tl_ice1, Tl_ice2, To_ice1, To_ice2;
   float co_turb, ce, cq_latent, cq_rain, rho_air, r_qviwv;

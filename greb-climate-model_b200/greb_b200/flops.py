@@ -68,7 +68,7 @@ def bytes_per_member_year(shared_corrections: bool = False) -> dict:
     return {
         "fluxcorr_read": 0 if shared_corrections else 3 * NT * F,
         "monthly_written": 60 * F,
-        "forcing_per_gpu_year": 8 * NT * F + NT * YD * 4,
+        "forcing_per_gpu_year": 10 * NT * F + NT * YD * 4,   # 10 per-step fields (greb_types.h GF_*) + sw_solar
     }
 
 

@@ -102,7 +102,7 @@ def test_switch_rules(forcing):
     for m in range(3):
         ens.set_member(m, p, [680.0, 680.0])
     with pytest.raises(greb_b200.GrebError):
-        ens.set_switches(0, 64)                            # unknown bit
+        ens.set_switches(0, 256)                           # unknown bit
     ens.set_switches(1, greb_b200.lib.SW_NO_HYDRO)
     ens.init()
     with pytest.raises(greb_b200.GrebError):

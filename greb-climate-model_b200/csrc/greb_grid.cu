@@ -13,7 +13,9 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/greb_grid.h"
@@ -59,9 +61,11 @@ __device__ __forceinline__ float diff_x(const float* T, const float* w, int j, f
                1.f * (w[j + 2] * (T[j + 1] - T[j + 2]) + w[j + 3] * (T[j + 3] - T[j + 2]))));
 }
 
-__global__ void __launch_bounds__(GG_THREADS) greb_grid_substep_kernel(const GridArgs a) {
-  extern __shared__ float sm[];
-  const int nx = a.nx, ny = a.ny, k = a.r0 + blockIdx.x, tid = threadIdx.x;
+// one latitude row k, one sub-step: X (level L) -> Xnew (level L+1).  `peer` (may be null) = a second
+// destination for the new row, indexed like Xnew: the neighbour band's halo row in ITS buffer (peer memory
+// over NVLink; persistent path).  All threads of the CTA call it with the same k.
+__device__ __forceinline__ void grid_row_substep(const GridArgs& a, int k, float* sm, float* peer) {
+  const int nx = a.nx, ny = a.ny, tid = threadIdx.x;
   const int stride = nx + 6;
   float* T0 = sm + 3;               // the row as it entered the sub-step (padded)
   float* wp = sm + stride + 3;      // wz of the row (padded)
@@ -75,8 +79,10 @@ __global__ void __launch_bounds__(GG_THREADS) greb_grid_substep_kernel(const Gri
   const float* Uk = a.u + (size_t)k * nx;
   const float* Vk = a.v + (size_t)k * nx;
   float* Ok = a.Xnew + (size_t)k * nx;
+  // The circulating field is read with ld.global.cg (L2 only): in the persistent kernel the rows of level L
+  // were written by other CTAs — or by the neighbour GPU — while this SM's L1 may still hold level L-2.
   for (int j = tid; j < nx; j += GG_THREADS) {
-    T0[j] = Xk[j];
+    T0[j] = __ldcg(Xk + j);
     wp[j] = Wk[j];
   }
   __syncthreads();
@@ -96,29 +102,29 @@ __global__ void __launch_bounds__(GG_THREADS) greb_grid_substep_kernel(const Gri
       // ---- y part of the diffusion, f:587-590
       float dTy;
       if (k >= 1 && k <= ny - 2)
-        dTy = a.ccy_d * (Wm1[j] * (Xm1[j] - T) + Wp1[j] * (Xp1[j] - T));
+        dTy = a.ccy_d * (Wm1[j] * (__ldcg(Xm1 + j) - T) + Wp1[j] * (__ldcg(Xp1 + j) - T));
       else if (k == 0)
-        dTy = a.ccy_d * Wp1[j] * (-T + Xp1[j]);
+        dTy = a.ccy_d * Wp1[j] * (-T + __ldcg(Xp1 + j));
       else
-        dTy = a.ccy_d * Wm1[j] * (Xm1[j] - T);
+        dTy = a.ccy_d * Wm1[j] * (__ldcg(Xm1 + j) - T);
       dd[c] = dTy;
       // ---- y part of the advection, f:756-795 (five row cases, different parenthesisation)
       const float vv = Vk[j];
       const float vm = vv >= 0.f ? vv : 0.f, vp = vv >= 0.f ? 0.f : vv;  // f:205-214
       float aTy;
       if (k == 0)
-        aTy = div3(a.ccy_a * (vp * (Wp1[j] * (T - Xp1[j]) + Wp2[j] * (T - Xp2[j]))));
+        aTy = div3(a.ccy_a * (vp * (Wp1[j] * (T - __ldcg(Xp1 + j)) + Wp2[j] * (T - __ldcg(Xp2 + j)))));
       else if (k == 1)
-        aTy = a.ccy_a * (-vm * (Wm1[j] * (T - Xm1[j])) +
-                         div3(vp * (Wp1[j] * (T - Xp1[j]) + Wp2[j] * (T - Xp2[j]))));
+        aTy = a.ccy_a * (-vm * (Wm1[j] * (T - __ldcg(Xm1 + j))) +
+                         div3(vp * (Wp1[j] * (T - __ldcg(Xp1 + j)) + Wp2[j] * (T - __ldcg(Xp2 + j)))));
       else if (k <= ny - 3)
-        aTy = div3(a.ccy_a * (-vm * (Wm1[j] * (T - Xm1[j]) + Wm2[j] * (T - Xm2[j])) +
-                              vp * (Wp1[j] * (T - Xp1[j]) + Wp2[j] * (T - Xp2[j]))));
+        aTy = div3(a.ccy_a * (-vm * (Wm1[j] * (T - __ldcg(Xm1 + j)) + Wm2[j] * (T - __ldcg(Xm2 + j))) +
+                              vp * (Wp1[j] * (T - __ldcg(Xp1 + j)) + Wp2[j] * (T - __ldcg(Xp2 + j)))));
       else if (k == ny - 2)
-        aTy = a.ccy_a * (div3(-vm * (Wm1[j] * (T - Xm1[j]) + Wm2[j] * (T - Xm2[j]))) +
-                         vp * (Wp1[j] * (T - Xp1[j])));
+        aTy = a.ccy_a * (div3(-vm * (Wm1[j] * (T - __ldcg(Xm1 + j)) + Wm2[j] * (T - __ldcg(Xm2 + j)))) +
+                         vp * (Wp1[j] * (T - __ldcg(Xp1 + j))));
       else
-        aTy = div3(a.ccy_a * (-vm * (Wm1[j] * (T - Xm1[j]) + Wm2[j] * (T - Xm2[j]))));
+        aTy = div3(a.ccy_a * (-vm * (Wm1[j] * (T - __ldcg(Xm1 + j)) + Wm2[j] * (T - __ldcg(Xm2 + j)))));
       adv[c] = aTy;
     }
   }
@@ -208,7 +214,120 @@ __global__ void __launch_bounds__(GG_THREADS) greb_grid_substep_kernel(const Gri
 #pragma unroll
   for (int c = 0; c < GG_MAXC; ++c) {
     const int j = tid + c * GG_THREADS;
-    if (j < nx) Ok[j] = T0[j] + dd[c] + adv[c];  // f:549
+    if (j < nx) {
+      const float r = T0[j] + dd[c] + adv[c];  // f:549
+      Ok[j] = r;
+      if (peer) peer[(size_t)k * nx + j] = r;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(GG_THREADS) greb_grid_substep_kernel(const GridArgs a) {
+  extern __shared__ float sm[];
+  grid_row_substep(a, a.r0 + blockIdx.x, sm, nullptr);
+}
+
+// ------------------------------------------------------------------------------------------------
+//   Persistent path: ONE cooperative launch advances the band (one or two fields) n sub-steps.
+//   Work item = (field, row); a CTA takes items blockIdx.x, blockIdx.x + gridDim.x, ... in an order that
+//   starts with the band's boundary rows (so the neighbours get them early) and the rows with the most
+//   polar sub-sub-steps.  Between sub-steps: a grid barrier (generation counter in global memory).
+//   Halo exchange without the host: the CTA that computes one of the band's two outermost rows stores the
+//   new row ALSO into the neighbour band's halo row (peer memory, NVLink) and then releases a per-row
+//   flag in the neighbour's memory with the new level; the CTA that computes a row next to a halo
+//   acquires the two flags of that side before it reads the halo rows.  A neighbour never overwrites
+//   halo rows that are still being read: it can only compute level L+1 after it has seen MY level-L flags,
+//   which I release after computing the rows that read its level L-1 rows.
+// ------------------------------------------------------------------------------------------------
+struct PField {
+  const float* X[2];        // level L in X[L & 1]; pointers shifted to GLOBAL row indexing
+  float* Xw[2];
+  const float *wz, *u, *v;
+  float* nbX[2][2];         // [side 0 = south, 1 = north][buffer]: neighbour's field buffers (global-row shifted), or null
+  int* nbflags[2];          // neighbour's flag words that I write: its side (1 - side), rows 0..1
+  volatile int* myflags;    // [2 sides][2 rows] written by my neighbours
+};
+struct PArgs {
+  GridArgs g;               // geometry (X/Xnew/wz/u/v filled per item)
+  PField f[2];
+  int nfields, k0, k1, level0, nsub, nitems;
+  const int* order;         // [nitems] field * 65536 + row
+  unsigned* bar;            // [0] arrival count, [1] generation
+  int* error;               // set to 1 if a wait timed out
+  long long timeout;        // cycles
+};
+
+__device__ __forceinline__ int ld_acquire_sys(const volatile int* p) {
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(int* p, int v) {
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ void grid_barrier(const PArgs& a) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    volatile unsigned* gen = a.bar + 1;
+    const unsigned g = *gen;
+    __threadfence();
+    if (atomicAdd(a.bar, 1u) == gridDim.x - 1) {
+      a.bar[0] = 0;
+      __threadfence();
+      atomicAdd(a.bar + 1, 1u);
+    } else {
+      const long long t0 = clock64();
+      while (*gen == g) {
+        if (clock64() - t0 > a.timeout) {
+          *a.error = 1;
+          break;
+        }
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(GG_THREADS, 2) greb_grid_persistent_kernel(const PArgs a) {
+  extern __shared__ float sm[];
+  GridArgs g = a.g;
+  for (int n = 0; n < a.nsub; ++n) {
+    const int L = a.level0 + n;
+    for (int it = blockIdx.x; it < a.nitems; it += gridDim.x) {
+      const int code = a.order[it];
+      const PField& f = a.f[code >> 16];
+      const int k = code & 0xffff;
+      const int side = (k < a.k0 + 2) ? 0 : (k >= a.k1 - 2 ? 1 : -1);
+      float* peer = nullptr;
+      if (side >= 0 && f.nbX[side][0]) {
+        if (threadIdx.x == 0) {   // the neighbour's rows of level L must have landed in my halo
+          const long long t0 = clock64();
+          while (ld_acquire_sys(f.myflags + side * 2) < L || ld_acquire_sys(f.myflags + side * 2 + 1) < L) {
+            if (clock64() - t0 > a.timeout) {
+              *a.error = 1;
+              break;
+            }
+          }
+        }
+        peer = f.nbX[side][(L + 1) & 1];
+      }
+      __syncthreads();            // flag seen by thread 0 -> everybody; also: the previous item's smem is free
+      g.X = f.X[L & 1];
+      g.Xnew = f.Xw[(L + 1) & 1];
+      g.wz = f.wz;
+      g.u = f.u;
+      g.v = f.v;
+      grid_row_substep(g, k, sm, peer);
+      if (peer) {
+        __threadfence_system();   // my stores into the neighbour's memory are visible system-wide ...
+        __syncthreads();
+        if (threadIdx.x == 0)     // ... before the flag that announces them
+          st_release_sys(f.nbflags[side] + (side == 0 ? k - a.k0 : k - (a.k1 - 2)), L + 1);
+      }
+    }
+    grid_barrier(a);
   }
 }
 
@@ -229,6 +348,15 @@ struct greb_grid_handle_s {
   float last_ms = 0.f;
   int last_launches = 0;
   bool pending = false;  // an asynchronous batch whose elapsed time has not been read yet
+  // persistent path
+  int* d_flags = nullptr;      // [0..3] halo flags written by the neighbours ([side][row]), [4] error word
+  unsigned* d_bar = nullptr;   // grid barrier (leader handle of a group)
+  int* d_order = nullptr;      // work-item order (leader handle)
+  int order_items = 0, order_fields = 0;
+  int level = 0;               // sub-steps done since set_fields
+  float* nbX[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // neighbour buffers opened through CUDA IPC
+  int* nbflags[2] = {nullptr, nullptr};
+  int nb_kbase[2] = {0, 0};
   std::string err;
 };
 
@@ -287,6 +415,10 @@ extern "C" int greb_grid_create(greb_grid_t* out, int nx, int ny, int k0, int k1
   for (float** p : gp) ok = ok && cudaMalloc((void**)p, (size_t)ny * sizeof(float)) == cudaSuccess;
   int** ip[] = {&h->d_polar, &h->d_t2d, &h->d_t2a};
   for (int** p : ip) ok = ok && cudaMalloc((void**)p, (size_t)ny * sizeof(int)) == cudaSuccess;
+  ok = ok && cudaMalloc((void**)&h->d_flags, 16 * sizeof(int)) == cudaSuccess &&
+       cudaMemset(h->d_flags, 0, 16 * sizeof(int)) == cudaSuccess;
+  ok = ok && cudaMalloc((void**)&h->d_bar, 4 * sizeof(unsigned)) == cudaSuccess &&
+       cudaMemset(h->d_bar, 0, 4 * sizeof(unsigned)) == cudaSuccess;
   if (!ok) {
     g_grid_err = "greb_grid_create: CUDA allocation failed";
     greb_grid_destroy(h);
@@ -300,8 +432,13 @@ extern "C" int greb_grid_destroy(greb_grid_t h) {
   if (!h) return -1;
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
+  for (int sd = 0; sd < 2; ++sd) {
+    for (int b = 0; b < 2; ++b)
+      if (h->nbX[sd][b]) cudaIpcCloseMemHandle(h->nbX[sd][b]);
+    if (h->nbflags[sd]) cudaIpcCloseMemHandle(h->nbflags[sd]);
+  }
   void* ptrs[] = {h->d_X[0], h->d_X[1], h->d_wz, h->d_u, h->d_v, h->d_ccx_diff, h->d_ccx_adv, h->d_ccx2_diff,
-                  h->d_ccx2_adv, h->d_polar, h->d_t2d, h->d_t2a};
+                  h->d_ccx2_adv, h->d_polar, h->d_t2d, h->d_t2a, h->d_flags, h->d_bar, h->d_order};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -377,7 +514,9 @@ extern "C" int greb_grid_set_fields(greb_grid_t h, const float* X, const float* 
   GCK(cudaMemcpy(h->d_wz, wz + off, fb, cudaMemcpyHostToDevice));
   GCK(cudaMemcpy(h->d_u, u + off, fb, cudaMemcpyHostToDevice));
   GCK(cudaMemcpy(h->d_v, v + off, fb, cudaMemcpyHostToDevice));
+  GCK(cudaMemset(h->d_flags, 0, 16 * sizeof(int)));
   h->cur = 0;
+  h->level = 0;
   h->valid_lo = h->kbase;
   h->valid_hi = h->kbase + h->nrows;
   h->have_fields = true;
@@ -447,12 +586,182 @@ extern "C" int greb_grid_substeps_async(greb_grid_t h, int n) {
     greb_grid_substep_kernel<<<hi - lo, GG_THREADS, smem, h->stream>>>(a);
     h->last_launches++;
     h->cur ^= 1;
+    h->level++;          // invariant: the current level lives in d_X[level & 1] (the persistent path relies on it)
     h->valid_lo = lo;
     h->valid_hi = hi;
   }
   GCK(cudaEventRecord(h->ev1, h->stream));
   GCK(cudaGetLastError());
   h->pending = true;
+  return 0;
+}
+
+// ---- persistent path: IPC plumbing + the cooperative launch ----------------------------------------
+struct GridIpcBlob {
+  cudaIpcMemHandle_t X[2], flags;
+  int kbase, nrows, nx, k0, k1, pad[3];
+};
+
+extern "C" int greb_grid_ipc_bytes(void) { return (int)sizeof(GridIpcBlob); }
+
+extern "C" int greb_grid_ipc_export(greb_grid_t h, void* out) {
+  if (!h || !out) return -1;
+  cudaSetDevice(h->device);
+  GridIpcBlob b;
+  memset(&b, 0, sizeof b);
+  GCK(cudaIpcGetMemHandle(&b.X[0], h->d_X[0]));
+  GCK(cudaIpcGetMemHandle(&b.X[1], h->d_X[1]));
+  GCK(cudaIpcGetMemHandle(&b.flags, h->d_flags));
+  b.kbase = h->kbase;
+  b.nrows = h->nrows;
+  b.nx = h->nx;
+  b.k0 = h->k0;
+  b.k1 = h->k1;
+  memcpy(out, &b, sizeof b);
+  return 0;
+}
+
+extern "C" int greb_grid_ipc_import(greb_grid_t h, int side, const void* in) {
+  if (!h || !in || side < 0 || side > 1) return h ? gfail(h, "greb_grid_ipc_import: bad arguments") : -1;
+  cudaSetDevice(h->device);
+  GridIpcBlob b;
+  memcpy(&b, in, sizeof b);
+  if (b.nx != h->nx || (side == 0 ? b.k1 != h->k0 : b.k0 != h->k1))
+    return gfail(h, "greb_grid_ipc_import: that band is not the neighbour on this side");
+  // the neighbour must store my two outermost rows as halo rows
+  if (side == 0 ? b.kbase + b.nrows < h->k0 + 2 : b.kbase > h->k1 - 2)
+    return gfail(h, "greb_grid_ipc_import: the neighbour's halo is thinner than 2 rows");
+  for (int i = 0; i < 2; ++i) {
+    void* p = nullptr;
+    GCK(cudaIpcOpenMemHandle(&p, b.X[i], cudaIpcMemLazyEnablePeerAccess));
+    h->nbX[side][i] = (float*)p;
+  }
+  void* p = nullptr;
+  GCK(cudaIpcOpenMemHandle(&p, b.flags, cudaIpcMemLazyEnablePeerAccess));
+  h->nbflags[side] = (int*)p;
+  h->nb_kbase[side] = b.kbase;
+  return 0;
+}
+
+extern "C" int greb_grid_run_persistent(greb_grid_t* hs, int nfields, int n) {
+  if (!hs || nfields < 1 || nfields > 2 || !hs[0]) return -1;
+  greb_grid_t h = hs[0];
+  for (int f = 0; f < nfields; ++f) {
+    greb_grid_t g = hs[f];
+    if (!g || g->device != h->device || g->nx != h->nx || g->ny != h->ny || g->k0 != h->k0 || g->k1 != h->k1 ||
+        g->kbase != h->kbase || g->level != h->level)
+      return gfail(h, "greb_grid_run_persistent: the handles of a group must be the same band at the same level");
+    if (!g->have_geo || !g->have_fields) return gfail(h, "greb_grid_run_persistent: geometry and fields must be set first");
+    if (g->cur != (g->level & 1)) return gfail(h, "greb_grid_run_persistent: internal: buffer parity lost");
+    if ((g->k0 > 0 && (g->halo < 2 || !g->nbX[0][0])) || (g->k1 < g->ny && (g->halo < 2 || !g->nbX[1][0])))
+      return gfail(h, "greb_grid_run_persistent: an inner band needs halo_rows >= 2 and both neighbours imported");
+  }
+  if (n < 0) return gfail(h, "greb_grid_run_persistent: n < 0");
+  if (h->k1 - h->k0 < 4 && (h->k0 > 0 || h->k1 < h->ny)) return gfail(h, "greb_grid_run_persistent: bands need >= 4 rows");
+  cudaSetDevice(h->device);
+  if (h->pending) {
+    const int rc = greb_grid_sync(h);
+    if (rc != 0) return rc;
+  }
+  // work-item order: boundary rows first (their results travel to the neighbours), then by the number of
+  // polar sub-sub-steps (the longest rows start first), then south to north
+  if (!h->d_order || h->order_fields != nfields) {
+    std::vector<int> t2(h->ny);
+    GCK(cudaMemcpy(t2.data(), h->d_t2d, h->ny * sizeof(int), cudaMemcpyDeviceToHost));
+    std::vector<std::pair<long, int>> keyed;
+    for (int f = 0; f < nfields; ++f)
+      for (int k = h->k0; k < h->k1; ++k) {
+        const bool edge = (h->k0 > 0 && k < h->k0 + 2) || (h->k1 < h->ny && k >= h->k1 - 2);
+        const long key = (edge ? 0 : 1) * 1000000L + (1000 - t2[k]) * 1000L + (k - h->k0);
+        keyed.push_back({key * 2 + f, f * 65536 + k});
+      }
+    std::sort(keyed.begin(), keyed.end());
+    std::vector<int> order;
+    for (auto& kv : keyed) order.push_back(kv.second);
+    if (h->d_order) cudaFree(h->d_order);
+    h->d_order = nullptr;
+    GCK(cudaMalloc((void**)&h->d_order, order.size() * sizeof(int)));
+    GCK(cudaMemcpy(h->d_order, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice));
+    h->order_items = (int)order.size();
+    h->order_fields = nfields;
+  }
+  PArgs a;
+  memset(&a, 0, sizeof a);
+  a.g.nx = h->nx;
+  a.g.ny = h->ny;
+  a.g.ccy_d = h->ccy_d;
+  a.g.ccy_a = h->ccy_a;
+  a.g.ccx_diff = h->d_ccx_diff;
+  a.g.ccx_adv = h->d_ccx_adv;
+  a.g.ccx2_diff = h->d_ccx2_diff;
+  a.g.ccx2_adv = h->d_ccx2_adv;
+  a.g.polar = h->d_polar;
+  a.g.t2d = h->d_t2d;
+  a.g.t2a = h->d_t2a;
+  for (int f = 0; f < nfields; ++f) {
+    greb_grid_t g = hs[f];
+    const ptrdiff_t shift = -(ptrdiff_t)g->kbase * g->nx;
+    // level L lives in buffer (cur ^ (L - level)) ; with cur the buffer of the current level:
+    // X[L & 1] must be the buffer of level L -> order the two buffers by the parity of the current level
+    float* cur = g->d_X[g->cur];
+    float* oth = g->d_X[g->cur ^ 1];
+    float* by_parity[2];
+    by_parity[g->level & 1] = cur;
+    by_parity[(g->level & 1) ^ 1] = oth;
+    for (int b = 0; b < 2; ++b) {
+      a.f[f].X[b] = by_parity[b] + shift;
+      a.f[f].Xw[b] = by_parity[b] + shift;
+    }
+    a.f[f].wz = g->d_wz + shift;
+    a.f[f].u = g->d_u + shift;
+    a.f[f].v = g->d_v + shift;
+    for (int sd = 0; sd < 2; ++sd) {
+      if (!g->nbX[sd][0]) continue;
+      // the neighbour keeps level L in ITS buffer of the same parity rule: its cur/level evolve in lockstep
+      // with mine (same number of sub-steps since set_fields), and both start with level 0 in d_X[0]
+      const ptrdiff_t nshift = -(ptrdiff_t)g->nb_kbase[sd] * g->nx;
+      a.f[f].nbX[sd][0] = g->nbX[sd][0] + nshift;
+      a.f[f].nbX[sd][1] = g->nbX[sd][1] + nshift;
+      a.f[f].nbflags[sd] = g->nbflags[sd] + (1 - sd) * 2;
+    }
+    a.f[f].myflags = g->d_flags;
+  }
+  a.nfields = nfields;
+  a.k0 = h->k0;
+  a.k1 = h->k1;
+  a.level0 = h->level;
+  a.nsub = n;
+  a.nitems = h->order_items;
+  a.order = h->d_order;
+  a.bar = h->d_bar;
+  a.error = h->d_flags + 4;
+  a.timeout = 6000000000LL;   // ~3 s at 2 GHz: a rank that never arrives ends the kernel instead of hanging the GPU
+  const size_t smem = (size_t)4 * (h->nx + 6) * sizeof(float);
+  int per_sm = 0, sms = 0;
+  GCK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, greb_grid_persistent_kernel, GG_THREADS, smem));
+  GCK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+  int grid = per_sm * sms;
+  if (grid > a.nitems) grid = a.nitems;
+  if (grid < 1) return gfail(h, "greb_grid_run_persistent: the kernel does not fit an SM");
+  GCK(cudaMemsetAsync(h->d_bar, 0, 4 * sizeof(unsigned), h->stream));
+  void* params[] = {&a};
+  GCK(cudaEventRecord(h->ev0, h->stream));
+  GCK(cudaLaunchCooperativeKernel((void*)greb_grid_persistent_kernel, dim3(grid), dim3(GG_THREADS), params, smem, h->stream));
+  GCK(cudaEventRecord(h->ev1, h->stream));
+  GCK(cudaStreamSynchronize(h->stream));
+  GCK(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+  h->last_launches = 1;
+  int err = 0;
+  GCK(cudaMemcpy(&err, h->d_flags + 4, sizeof(int), cudaMemcpyDeviceToHost));
+  for (int f = 0; f < nfields; ++f) {
+    greb_grid_t g = hs[f];
+    g->level += n;
+    if (n & 1) g->cur ^= 1;
+    // own rows are current; the halo rows hold the neighbours' rows of the same level (pushed by them)
+    g->valid_lo = g->kbase;
+    g->valid_hi = g->kbase + g->nrows;
+  }
+  if (err) return gfail(h, "greb_grid_run_persistent: a wait for a neighbour (or the grid barrier) timed out");
   return 0;
 }
 

@@ -24,7 +24,8 @@ from . import sharding
 
 GRID_SYMBOLS = ["greb_grid_create", "greb_grid_destroy", "greb_grid_last_error", "greb_grid_set_geometry",
                 "greb_grid_set_fields", "greb_grid_substeps", "greb_grid_substeps_async", "greb_grid_sync", "greb_grid_view", "greb_grid_halo_refreshed",
-                "greb_grid_get", "greb_grid_last_ms"]
+                "greb_grid_get", "greb_grid_last_ms", "greb_grid_ipc_bytes", "greb_grid_ipc_export", "greb_grid_ipc_import",
+                "greb_grid_run_persistent"]
 _grid = None
 
 
@@ -54,6 +55,10 @@ def load_grid_library():
     L.greb_grid_halo_refreshed.argtypes = [vp]
     L.greb_grid_get.argtypes = [vp, fp]
     L.greb_grid_last_ms.argtypes = [vp, fp, ip]
+    L.greb_grid_ipc_bytes.argtypes = []
+    L.greb_grid_ipc_export.argtypes = [vp, vp]
+    L.greb_grid_ipc_import.argtypes = [vp, C.c_int, vp]
+    L.greb_grid_run_persistent.argtypes = [C.POINTER(vp), C.c_int, C.c_int]
     _grid = L
     return L
 
@@ -139,6 +144,17 @@ class DeviceBand:
     def halo_refreshed(self):
         self._ck(self.L.greb_grid_halo_refreshed(self.h), "greb_grid_halo_refreshed")
 
+    def ipc_export(self) -> bytes:
+        """the blob a neighbour rank needs to map this band's buffers (CUDA IPC handles + geometry)"""
+        buf = C.create_string_buffer(self.L.greb_grid_ipc_bytes())
+        self._ck(self.L.greb_grid_ipc_export(self.h, buf), "greb_grid_ipc_export")
+        return buf.raw
+
+    def ipc_import(self, side: int, blob: bytes):
+        """map the south (side 0) / north (side 1) neighbour's buffers"""
+        buf = C.create_string_buffer(blob, len(blob))
+        self._ck(self.L.greb_grid_ipc_import(self.h, side, buf), "greb_grid_ipc_import")
+
     def get(self) -> np.ndarray:
         out = np.zeros((self.k1 - self.k0, self.nx), dtype=np.float32)
         self._ck(self.L.greb_grid_get(self.h, _lib._p(out)), "greb_grid_get")
@@ -213,3 +229,43 @@ def advance_overlapped(bands, n_substeps: int, rank: int = 0, world: int = 1, gr
     for b in bands:
         b.sync()
     return exchanges
+
+
+class PersistentGroup:
+    """The persistent path (include/greb_grid.h greb_grid_run_persistent): the fields of one band — up to two
+    DeviceBands with the same rows, created with s = 1, i.e. 2 halo rows — advance together in ONE
+    cooperative launch per call; halo rows travel GPU to GPU inside the kernel (peer stores + flags), the
+    host only swaps the CUDA IPC handles once."""
+
+    def __init__(self, bands, rank: int = 0, world: int = 1, group=None):
+        self.bands, self.rank, self.world = list(bands), rank, world
+        if not 1 <= len(self.bands) <= 2:
+            raise ValueError("a group holds one or two fields")
+        self.L = self.bands[0].L
+        self.kernel_ms = 0.0
+        self.launches = 0
+        if world > 1:
+            connect_neighbours(self.bands, rank, world, group)
+
+    def advance(self, n: int):
+        arr = (C.c_void_p * len(self.bands))(*[b.h for b in self.bands])
+        rc = self.L.greb_grid_run_persistent(arr, len(self.bands), n)
+        self.bands[0]._ck(rc, "greb_grid_run_persistent")
+        ms, nl = C.c_float(), C.c_int()
+        self.L.greb_grid_last_ms(self.bands[0].h, C.byref(ms), C.byref(nl))
+        self.kernel_ms += ms.value
+        self.launches += nl.value
+
+
+def connect_neighbours(bands, rank: int, world: int, group=None):
+    """every rank publishes one IPC blob per field; rank r imports those of r-1 (south) and r+1 (north)"""
+    import torch.distributed as dist
+    mine = [b.ipc_export() for b in bands]
+    everyone = [None] * world
+    dist.all_gather_object(everyone, mine, group=group)
+    for f, b in enumerate(bands):
+        if rank > 0:
+            b.ipc_import(0, everyone[rank - 1][f])
+        if rank < world - 1:
+            b.ipc_import(1, everyone[rank + 1][f])
+    dist.barrier(group=group)

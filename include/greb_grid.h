@@ -50,6 +50,24 @@ int greb_grid_view(greb_grid_t h, float** dev_rows, int* kbase, int* nrows, int*
 /* call after the neighbours' rows were written into the halo rows of the current buffer */
 int greb_grid_halo_refreshed(greb_grid_t h);
 
+/* ---- persistent path: no kernel launch per sub-step, no host in the exchange ---------------------------
+ * greb_grid_run_persistent advances a GROUP of one or two handles of the same band (the two independent
+ * fields of a step, air temperature and humidity, src/greb.f90:299-304) by n sub-steps in ONE cooperative
+ * launch: work item = (field, row), a grid barrier between sub-steps, and the halo exchange done by the
+ * kernel itself — the CTA that computes one of the band's two outermost rows stores the new row also into
+ * the neighbour band's halo row (peer memory over NVLink) and releases a per-row level flag there; the CTA
+ * that computes a row next to a halo acquires those flags first.  Needs halo_rows >= 2 (exactly the reach
+ * of a sub-step, f:587-590, 771-780: nothing is recomputed redundantly).
+ * The neighbours' buffers are mapped with CUDA IPC: every rank exports a blob (greb_grid_ipc_bytes bytes)
+ * per handle, the host side swaps the blobs (torch.distributed all_gather_object in greb_b200/bigrid.py)
+ * and imports its south (side 0) and north (side 1) neighbour's.  All ranks must call set_fields, then
+ * synchronise (a host barrier), then call run_persistent with the same n; a rank that never arrives makes
+ * the others' waits time out (error return) instead of hanging the GPU. */
+int greb_grid_ipc_bytes(void);
+int greb_grid_ipc_export(greb_grid_t h, void* blob);
+int greb_grid_ipc_import(greb_grid_t h, int side, const void* neighbour_blob);
+int greb_grid_run_persistent(greb_grid_t* handles, int nfields, int n);
+
 /* the band's own rows [k0, k1) -> host [k1-k0][xdim] */
 int greb_grid_get(greb_grid_t h, float* out);
 /* CUDA-event time of the last greb_grid_substeps call and its kernel launches */

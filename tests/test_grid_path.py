@@ -234,3 +234,82 @@ def test_overlapped_fields_equal_sequential_runs():
         b.close()
     assert np.array_equal(got[0], og.substeps(g, X, wz, u, v, n))
     assert np.array_equal(got[1], og.substeps(g, wz, wz, u, v, n))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nx,ny,n", [(96, 48, 24), (192, 96, 11), (1440, 720, 6)])
+def test_persistent_kernel_equals_the_launch_per_substep_path(nx, ny, n):
+    """one cooperative launch (grid barrier between sub-steps, two fields as work items) == n launches, bit for bit;
+    the two paths can alternate on one handle (buffer parity is kept)"""
+    X, wz, u, v = fields(nx, ny, seed=nx)
+    g = og.Geometry(nx, ny)
+    want = [og.substeps(g, X, wz, u, v, n + 3), og.substeps(g, wz, wz, u, v, n + 3)]
+    pair = [bigrid.DeviceBand(nx, ny, 0, ny, 1), bigrid.DeviceBand(nx, ny, 0, ny, 1)]
+    pair[0].set_fields(X, wz, u, v)
+    pair[1].set_fields(wz, wz, u, v)
+    grp = bigrid.PersistentGroup(pair)
+    grp.advance(n)
+    assert grp.launches == 1 and grp.kernel_ms > 0
+    for b in pair:                                   # 3 more sub-steps on the v1 path, then nothing breaks
+        bigrid.advance(b, 3)
+    got = [b.get() for b in pair]
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+    grp.advance(2)                                   # and back to the persistent path
+    assert np.array_equal(pair[0].get(), og.substeps(g, X, wz, u, v, n + 5))
+    single = bigrid.DeviceBand(nx, ny, 0, ny, 1)     # a group of one field
+    single.set_fields(X, wz, u, v)
+    bigrid.PersistentGroup([single]).advance(n + 5)
+    assert np.array_equal(single.get(), pair[0].get())
+    for b in pair + [single]:
+        b.close()
+
+
+@pytest.mark.gpu
+def test_persistent_inner_band_without_neighbours_is_refused():
+    b = bigrid.DeviceBand(192, 96, 24, 48, 1)
+    X, wz, u, v = fields(192, 96)
+    b.set_fields(X, wz, u, v)
+    with pytest.raises(greb_b200_error()):
+        bigrid.PersistentGroup([b]).advance(1)
+    b.close()
+
+
+def _ipc_worker(rank, world, port, ret):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    class FakeBand:                                  # what connect_neighbours needs of a DeviceBand
+        def __init__(self, f):
+            self.f, self.imported = f, {}
+        def ipc_export(self):
+            return f"blob-rank{rank}-field{self.f}".encode()
+        def ipc_import(self, side, blob):
+            self.imported[side] = blob.decode()
+    try:
+        bands = [FakeBand(0), FakeBand(1)]
+        bigrid.connect_neighbours(bands, rank, world)
+        ret[rank] = [b.imported for b in bands]
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_neighbour_handle_exchange_gloo_world3():
+    """the host side of the persistent path: every rank ends up with its south and north neighbours' blobs"""
+    import torch.multiprocessing as mp
+    world = 3
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ret = mp.Manager().dict()
+    mp.spawn(_ipc_worker, args=(world, port, ret), nprocs=world, join=True)
+    for r in range(world):
+        for f in range(2):
+            want = {}
+            if r > 0:
+                want[0] = f"blob-rank{r - 1}-field{f}"
+            if r < world - 1:
+                want[1] = f"blob-rank{r + 1}-field{f}"
+            assert ret[r][f] == want, (r, f, ret[r][f])

@@ -53,6 +53,10 @@ def main():
     ap.add_argument("--period", dest="s", type=int, default=16, help="sub-steps between halo exchanges (halo = 2*s rows)")
     ap.add_argument("--verify", type=int, default=48, help="sub-steps of the N-GPU == 1-GPU check (0 = skip)")
     ap.add_argument("--no-overlap", action="store_true", help="advance the two fields one after the other")
+    ap.add_argument("--persistent", action="store_true",
+                    help="v2 path: one cooperative launch per call, both fields in it, halo rows pushed GPU to GPU by "
+                         "the kernel (CUDA IPC peer memory + flags); the host is not in the loop (--period is ignored)")
+    ap.add_argument("--chunk", type=int, default=1350, help="--persistent: sub-steps per cooperative launch")
     args = ap.parse_args()
 
     import torch
@@ -71,7 +75,7 @@ def main():
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    nx, ny, s = args.nx, args.ny, args.s
+    nx, ny, s = args.nx, args.ny, (1 if args.persistent else args.s)
     f = synth.cached_forcing(cache_dir=os.environ.get("GREB_FORCING_CACHE", "/tmp/greb_b200_cache"))
     ityr = 200
     topo = upsample(f.z_topo, ny, nx)
@@ -95,8 +99,14 @@ def main():
     # ---- correctness before timing -----------------------------------------------------------
     if args.verify > 0:
         b = make("Ta", k0, k1)
-        bigrid.advance(b, args.verify, rank, world)
+        if args.persistent:
+            grp = bigrid.PersistentGroup([b], rank, world)
+            barrier()                                          # every rank has set its fields (and cleared its flags)
+            grp.advance(args.verify)
+        else:
+            bigrid.advance(b, args.verify, rank, world)
         mine = torch.from_numpy(b.get()).to(f"cuda:{local}")
+        barrier()                                              # nobody unmaps buffers a neighbour still writes
         b.close()
         if world > 1:                                          # gather the bands on every rank (padded: ragged heights)
             sizes = [bigrid.band_range(ny, world, r) for r in range(world)]
@@ -118,19 +128,33 @@ def main():
     bands = {n: make(n, k0, k1) for n in ("Ta", "q")}
     nsub = bands["Ta"].nsub
     n_time = max(s, int(round(args.steps * nsub)))
-    for b in bands.values():                                    # warm-up: 3 exchange periods
-        bigrid.advance(b, 3 * s, rank, world)
-        b.kernel_ms, b.launches = 0.0, 0
+    grp = None
+    if args.persistent:
+        grp = bigrid.PersistentGroup(list(bands.values()), rank, world)
+        barrier()
+        grp.advance(48)                                         # warm-up
+        grp.kernel_ms, grp.launches = 0.0, 0
+        n_time = max(1, int(round(args.steps * nsub)))
+    else:
+        for b in bands.values():                                # warm-up: 3 exchange periods
+            bigrid.advance(b, 3 * s, rank, world)
+            b.kernel_ms, b.launches = 0.0, 0
     barrier()
     t0 = time.perf_counter()
-    if args.no_overlap:
+    if grp is not None:
+        exchanges, done = 0, 0
+        while done < n_time:                                    # a few cooperative launches, no host work between sub-steps
+            m = min(args.chunk, n_time - done)
+            grp.advance(m)
+            done += m
+    elif args.no_overlap:
         exchanges = sum(bigrid.advance(b, n_time, rank, world) for b in bands.values())
     else:                                                       # one field's exchange behind the other's sub-steps
         exchanges = bigrid.advance_overlapped(list(bands.values()), n_time, rank, world)
     barrier()
     wall = time.perf_counter() - t0
-    kms = sum(b.kernel_ms for b in bands.values())
-    launches = sum(b.launches for b in bands.values())
+    kms = grp.kernel_ms if grp is not None else sum(b.kernel_ms for b in bands.values())
+    launches = grp.launches if grp is not None else sum(b.launches for b in bands.values())
     mean_T = float(bands["Ta"].get().astype(np.float64).mean())
     t = torch.tensor([wall, kms], dtype=torch.float64, device=f"cuda:{local}")
     m = torch.tensor([mean_T * (k1 - k0)], dtype=torch.float64, device=f"cuda:{local}")
@@ -148,9 +172,14 @@ def main():
                        "substeps_per_circulation": nsub, "dt_crcl_s": bands["Ta"].dt_crcl,
                        "substeps_between_exchanges": s, "halo_rows": 2 * s,
                        "rules": "R1 dt_crcl = 1800*(48/ydim)^2; R2 |lat| clamped to 88.125 deg in dxlat, dtdff2 >= 1 s",
-                       "exchange": "NCCL point-to-point of 2*s rows per neighbour every s sub-steps; "
-                                   "all-reduce of the global mean at the end",
-                       "overlap": "none" if args.no_overlap else "the exchange of one field runs behind the sub-steps of the other"},
+                       "exchange": ("inside the persistent kernel: the two outermost rows of each band are stored into the "
+                                    "neighbour's halo rows (CUDA IPC peer memory over NVLink) + per-row release/acquire "
+                                    "flags, every sub-step; all-reduce of the global mean at the end" if grp is not None else
+                                    "NCCL point-to-point of 2*s rows per neighbour every s sub-steps; "
+                                    "all-reduce of the global mean at the end"),
+                       "path": "persistent cooperative kernel (v2)" if grp is not None else "one launch per sub-step (v1)",
+                       "overlap": ("both fields in one kernel" if grp is not None else
+                                   "none" if args.no_overlap else "the exchange of one field runs behind the sub-steps of the other")},
             "timed_substeps_per_field": n_time, "wall_s": wall, "kernel_s_max_rank": kms / 1e3,
             "cell_substeps_per_s": 2 * n_time * nx * ny / wall,
             "gpu_launches_rank0": launches, "halo_exchanges_rank0": exchanges,
@@ -158,6 +187,7 @@ def main():
             "global_mean_Ta": float(m[0]) / ny, "checks": checks,
         }
         print(json.dumps(line), flush=True)
+    barrier()
     for b in bands.values():
         b.close()
     if world > 1:

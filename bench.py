@@ -242,6 +242,8 @@ def main():
                          "restated on the device — whole runs are bit-identical to the reference arithmetic; "
                          "fast: factored stencils + FMA + approximate division/log/exp (NOT within the 0.01 K gate "
                          "for low-CO2 perturbed members over 50 years: tests/test_gpu_long_parity.py)")
+    ap.add_argument("--no-bigrid", action="store_true",
+                    help="skip the strong-scaling block of BASELINE.json configs[4] (one 0.25-degree member in bands)")
     ap.add_argument("--quick", action="store_true",
                     help="kernel experiments: skip the exact-mode, single-run and CPU-baseline extras")
     ap.add_argument("--shared-physics", action="store_true",
@@ -336,6 +338,13 @@ def main():
     # ensemble mean / variance FIELDS of the last year's monthly means (untimed): reduced over the rank's members
     # on the device, then over the ranks with one NCCL reduce to rank 0 (greb_b200/sharding.py)
     f_mean, f_var, f_cnt = sharding.reduce_field_moments(ens, M, dst=0)
+
+    # BASELINE.json configs[4] (strong scaling): one 1440x720 member in latitude bands over the same N GPUs,
+    # persistent kernel with in-kernel halo exchange; 0.1 of a step timed (greb_b200/bigrid.py)
+    bigrid_line = None
+    if not (args.quick or args.no_bigrid or os.environ.get("GREB_BENCH_BIGRID") == "0"):
+        from greb_b200 import bigrid
+        bigrid_line = bigrid.bench_persistent(forcing, rank, world, local)
 
     t = torch.tensor([ev_ms, wall_s * 1e3], device=f"cuda:{local}", dtype=torch.float64)
     if world > 1:
@@ -441,6 +450,7 @@ def main():
             "ensemble_stats": {"sum_gmean": float(stats[0]), "sum_gmean_coslat": float(stats[1]),
                                "sumsq_gmean": float(stats[2])},
             "nonfinite_members": int(ens.flags().sum()),
+            "bigrid": bigrid_line,
             "ensemble_fields": {"members": int(f_cnt), "december_tsurf_mean_K": float(f_mean[11, 0].mean()),
                                 "december_tsurf_max_std_K": float(np.sqrt(f_var[11, 0].max())),
                                 "note": "ensemble mean/variance of the 12 x 5 monthly fields: device reduction per rank + "

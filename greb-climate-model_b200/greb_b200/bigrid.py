@@ -63,6 +63,23 @@ def load_grid_library():
     return L
 
 
+def upsample(a: np.ndarray, ny: int, nx: int) -> np.ndarray:
+    """bilinear upsample of a [48][96] cell-centred field (periodic in longitude, clamped at the poles)"""
+    sy, sx = a.shape
+    y = (np.arange(ny) + 0.5) * sy / ny - 0.5
+    x = (np.arange(nx) + 0.5) * sx / nx - 0.5
+    y0 = np.clip(np.floor(y).astype(int), 0, sy - 1)
+    y1 = np.clip(y0 + 1, 0, sy - 1)
+    fy = np.clip(y - np.floor(y), 0, 1).astype(np.float32)
+    fy = np.where(np.floor(y) < 0, 0.0, fy).astype(np.float32)
+    x0 = np.floor(x).astype(int) % sx
+    x1 = (x0 + 1) % sx
+    fx = (x - np.floor(x)).astype(np.float32)
+    top = a[y0][:, x0] * (1 - fx) + a[y0][:, x1] * fx
+    bot = a[y1][:, x0] * (1 - fx) + a[y1][:, x1] * fx
+    return np.ascontiguousarray(top * (1 - fy[:, None]) + bot * fy[:, None], dtype=np.float32)
+
+
 def band_range(ny: int, world: int, rank: int) -> Tuple[int, int]:
     """latitude rows [k0, k1) of `rank`: contiguous bands, heights differ by at most one"""
     return sharding.shard_range(ny, world, rank)
@@ -269,3 +286,96 @@ def connect_neighbours(bands, rank: int, world: int, group=None):
         if rank < world - 1:
             b.ipc_import(1, everyone[rank + 1][f])
     dist.barrier(group=group)
+
+
+def quarter_degree_fields(forcing, nx: int = 1440, ny: int = 720, ityr: int = 200):
+    """the synthetic 0.25-degree workload of BASELINE.json configs[4]: step `ityr` of the S0 climatologies
+    bilinearly upsampled -> {"Ta": (X, wz_air), "q": (X, wz_vapor)}, u, v"""
+    topo = upsample(forcing.z_topo, ny, nx)
+    fld = {"Ta": (upsample(forcing.tclim[ityr - 1], ny, nx), np.exp(-topo / np.float32(8400.0)).astype(np.float32)),
+           "q": (upsample(forcing.qclim[ityr - 1], ny, nx), np.exp(-topo / np.float32(5000.0)).astype(np.float32))}
+    return fld, upsample(forcing.uclim[ityr - 1], ny, nx), upsample(forcing.vclim[ityr - 1], ny, nx)
+
+
+def bench_persistent(forcing, rank: int, world: int, device: int, substeps: int = 540, nx: int = 1440, ny: int = 720):
+    """Strong-scaling measurement of the persistent path for bench.py: both fields of one 0.25-degree member,
+    latitude bands over `world` GPUs, `substeps` sub-steps per field timed after a 48-sub-step warm-up.
+    EVERY rank executes the same sequence of collectives whatever happens locally (a local failure is
+    carried in `ok` and reported, never turned into a missing collective).  Returns a dict on every rank."""
+    import time
+    import torch
+    import torch.distributed as dist
+    multi = world > 1 and dist.is_available() and dist.is_initialized()
+    ok, err, bands, grp = True, "", [], None
+
+    def sync():
+        torch.cuda.synchronize()
+        if multi:
+            dist.barrier()
+
+    try:
+        fld, u, v = quarter_degree_fields(forcing, nx, ny)
+        k0, k1 = band_range(ny, world, rank)
+        for name in ("Ta", "q"):
+            b = DeviceBand(nx, ny, k0, k1, 1, device=device)
+            b.set_fields(fld[name][0], fld[name][1], u, v)
+            bands.append(b)
+        blobs = [b.ipc_export() for b in bands]
+    except Exception as e:  # noqa: BLE001
+        ok, err, blobs = False, f"setup: {e}", [b"", b""]
+    everyone = [blobs]
+    if multi:
+        everyone = [None] * world
+        dist.all_gather_object(everyone, blobs)
+    try:
+        if ok and multi:
+            for f, b in enumerate(bands):
+                if rank > 0:
+                    b.ipc_import(0, everyone[rank - 1][f])
+                if rank < world - 1:
+                    b.ipc_import(1, everyone[rank + 1][f])
+        if ok:
+            grp = PersistentGroup(bands)
+    except Exception as e:  # noqa: BLE001
+        ok, err = False, f"ipc: {e}"
+    flag = torch.tensor([1.0 if ok else 0.0], device=f"cuda:{device}")
+    if multi:
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    all_ok = bool(flag.item() > 0.5)
+    wall = kms = 0.0
+    nsub = bands[0].nsub if bands else 0
+    if all_ok:
+        sync()                                              # every rank has set its fields and cleared its flags
+        try:
+            grp.advance(48)
+            grp.kernel_ms = 0.0
+        except Exception as e:  # noqa: BLE001
+            ok, err = False, f"warm-up: {e}"
+        sync()
+        t0 = time.perf_counter()
+        try:
+            if ok:
+                grp.advance(substeps)
+        except Exception as e:  # noqa: BLE001
+            ok, err = False, f"run: {e}"
+        sync()
+        wall = time.perf_counter() - t0
+        kms = grp.kernel_ms if grp else 0.0
+    t = torch.tensor([wall, kms, 1.0 if ok else 0.0], dtype=torch.float64, device=f"cuda:{device}")
+    if multi:
+        tm = t.clone()
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        wall, kms, okf = float(tm[0]), float(tm[1]), float(t[2])
+    else:
+        okf = float(t[2])
+    sync()
+    for b in bands:
+        b.close()
+    if not all_ok or okf < 0.5:
+        return {"error": err or "another rank failed"}
+    steps = substeps / nsub
+    return {"metric": "12-hour steps/s (both circulations of one 0.25-degree member)", "value": steps / (kms / 1e3),
+            "unit": "steps/s", "scaling": "strong", "n_gpus": world, "grid": f"{nx}x{ny}", "substeps_timed_per_field": substeps,
+            "substeps_per_circulation": nsub, "us_per_substep": 1e3 * kms / substeps, "wall_steps_per_s": steps / wall,
+            "path": "persistent cooperative kernel; halo rows pushed GPU to GPU inside the kernel (CUDA IPC + flags)"}

@@ -28,23 +28,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "greb-climate-model_b200"))
 
 
-def upsample(a: np.ndarray, ny: int, nx: int) -> np.ndarray:
-    """bilinear upsample of a [48][96] cell-centred field (periodic in longitude, clamped at the poles)"""
-    sy, sx = a.shape
-    y = (np.arange(ny) + 0.5) * sy / ny - 0.5
-    x = (np.arange(nx) + 0.5) * sx / nx - 0.5
-    y0 = np.clip(np.floor(y).astype(int), 0, sy - 1)
-    y1 = np.clip(y0 + 1, 0, sy - 1)
-    fy = np.clip(y - np.floor(y), 0, 1).astype(np.float32)
-    fy = np.where(np.floor(y) < 0, 0.0, fy).astype(np.float32)
-    x0 = np.floor(x).astype(int) % sx
-    x1 = (x0 + 1) % sx
-    fx = (x - np.floor(x)).astype(np.float32)
-    top = a[y0][:, x0] * (1 - fx) + a[y0][:, x1] * fx
-    bot = a[y1][:, x0] * (1 - fx) + a[y1][:, x1] * fx
-    return np.ascontiguousarray(top * (1 - fy[:, None]) + bot * fy[:, None], dtype=np.float32)
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--nx", type=int, default=1440)
@@ -62,6 +45,7 @@ def main():
     import torch
     import torch.distributed as dist
     from greb_b200 import bigrid, synth
+    upsample = bigrid.upsample
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -31,12 +32,6 @@ struct GridArgs {
   const float *ccx_diff, *ccx_adv, *ccx2_diff, *ccx2_adv;  // [ny]
   const int *polar, *t2d, *t2a;                            // [ny]
 };
-
-__device__ __forceinline__ void pad_fix(float* p, int nx) {  // p points at element 0 of a padded row
-  const int t = threadIdx.x;
-  if (t < 3) p[-3 + t] = p[nx - 3 + t];
-  else if (t < 6) p[nx + t - 3] = p[t - 3];
-}
 
 // Correctly rounded x/3 and x/20 without the division subroutine: q0 = x*RN(1/d); r = fma(-d,q0,x);
 // q = fma(r,RN(1/d),q0) equals RN(x/d) for every float x whose quotient is a normal number (the same
@@ -82,12 +77,18 @@ __device__ __forceinline__ void grid_row_substep(const GridArgs& a, int k, float
   // The circulating field is read with ld.global.cg (L2 only): in the persistent kernel the rows of level L
   // were written by other CTAs — or by the neighbour GPU — while this SM's L1 may still hold level L-2.
   for (int j = tid; j < nx; j += GG_THREADS) {
-    T0[j] = __ldcg(Xk + j);
-    wp[j] = Wk[j];
+    const float t = __ldcg(Xk + j), w = Wk[j];
+    T0[j] = t;
+    wp[j] = w;
+    if (j < 3) {                 // the periodic pads are written by the threads that own the wrapped cells:
+      T0[nx + j] = t;            // one barrier per pass instead of store / barrier / pad / barrier
+      wp[nx + j] = w;
+    }
+    if (j >= nx - 3) {
+      T0[j - nx] = t;
+      wp[j - nx] = w;
+    }
   }
-  __syncthreads();
-  pad_fix(T0, nx);
-  pad_fix(wp, nx);
   __syncthreads();
 
   const int polar = a.polar[k];
@@ -146,10 +147,11 @@ __device__ __forceinline__ void grid_row_substep(const GridArgs& a, int k, float
       for (int j = tid; j < nx; j += GG_THREADS) {
         float d = diff_x(cur, wp, j, cc);
         if (d <= -cur[j]) d = -0.9f * cur[j];  // f:715
-        nxt[j] = cur[j] + d;                   // f:716
+        const float r = cur[j] + d;            // f:716
+        nxt[j] = r;
+        if (j < 3) nxt[nx + j] = r;
+        if (j >= nx - 3) nxt[j - nx] = r;
       }
-      __syncthreads();
-      pad_fix(nxt, nx);
       __syncthreads();
       cur = nxt;
       nxt = (nxt == A) ? B : A;
@@ -196,10 +198,11 @@ __device__ __forceinline__ void grid_row_substep(const GridArgs& a, int k, float
                               up * (10.f * wp[jp1] * (cur[j] - cur[jp1]) + 4.f * wp[jp2] * (cur[jp1] - cur[jp2]) +
                                     1.f * wp[jp3] * (cur[jp2] - cur[jp3]))));
         if (d <= -cur[j]) d = -0.9f * cur[j];  // f:907
-        nxt[j] = cur[j] + d;                   // f:908
+        const float r = cur[j] + d;            // f:908
+        nxt[j] = r;
+        if (j < 3) nxt[nx + j] = r;
+        if (j >= nx - 3) nxt[j - nx] = r;
       }
-      __syncthreads();
-      pad_fix(nxt, nx);
       __syncthreads();
       cur = nxt;
       nxt = (nxt == A) ? B : A;
@@ -228,36 +231,37 @@ __global__ void __launch_bounds__(GG_THREADS) greb_grid_substep_kernel(const Gri
 }
 
 // ------------------------------------------------------------------------------------------------
-//   Persistent path: ONE cooperative launch advances the band (one or two fields) n sub-steps.
-//   Work item = (field, row); a CTA takes items blockIdx.x, blockIdx.x + gridDim.x, ... in an order that
-//   starts with the band's boundary rows (so the neighbours get them early) and the rows with the most
-//   polar sub-sub-steps.  Between sub-steps: a grid barrier (generation counter in global memory).
+//   Persistent path: ONE cooperative launch advances the band (one or two fields) n sub-steps with
+//   no barrier at all — a dataflow over (level, field, row) work items.
+//   Every row carries a level counter in global memory.  Row k may go from level L to L+1 as soon as the
+//   rows k-2..k+2 (those that exist) have reached level L: then they hold the values it reads, and they have
+//   finished reading the level L-1 values of row k that it is about to overwrite (double buffering).
+//   CTAs take items from ONE monotonic counter, level-major, within a level the longest rows first; an item
+//   only waits for items earlier in that order, which are already running on co-resident CTAs, so nothing
+//   can deadlock and a slow row (the pole rows iterate 8 times) delays only its neighbourhood, not the band.
 //   Halo exchange without the host: the CTA that computes one of the band's two outermost rows stores the
-//   new row ALSO into the neighbour band's halo row (peer memory, NVLink) and then releases a per-row
-//   flag in the neighbour's memory with the new level; the CTA that computes a row next to a halo
-//   acquires the two flags of that side before it reads the halo rows.  A neighbour never overwrites
-//   halo rows that are still being read: it can only compute level L+1 after it has seen MY level-L flags,
-//   which I release after computing the rows that read its level L-1 rows.
+//   new row ALSO into the neighbour band's halo row (peer memory, NVLink) and then releases that row's level
+//   counter in the neighbour's memory; the neighbour's rows next to the halo wait on it like on any other row.
 // ------------------------------------------------------------------------------------------------
 struct PField {
   const float* X[2];        // level L in X[L & 1]; pointers shifted to GLOBAL row indexing
   float* Xw[2];
   const float *wz, *u, *v;
-  float* nbX[2][2];         // [side 0 = south, 1 = north][buffer]: neighbour's field buffers (global-row shifted), or null
-  int* nbflags[2];          // neighbour's flag words that I write: its side (1 - side), rows 0..1
-  volatile int* myflags;    // [2 sides][2 rows] written by my neighbours
+  int* level;               // [stored rows] level of every row incl. the halo rows, global-row shifted
+  float* nbX[2][2];         // [side 0 = south, 1 = north][buffer]: neighbour's field buffers (shifted), or null
+  int* nblevel[2];          // neighbour's row-level array (shifted), or null
 };
 struct PArgs {
   GridArgs g;               // geometry (X/Xnew/wz/u/v filled per item)
   PField f[2];
   int nfields, k0, k1, level0, nsub, nitems;
-  const int* order;         // [nitems] field * 65536 + row
-  unsigned* bar;            // [0] arrival count, [1] generation
+  const int* order;         // [nitems] field * 65536 + row, longest rows first
+  unsigned* counter;        // the work counter
   int* error;               // set to 1 if a wait timed out
   long long timeout;        // cycles
 };
 
-__device__ __forceinline__ int ld_acquire_sys(const volatile int* p) {
+__device__ __forceinline__ int ld_acquire_sys(const int* p) {
   int v;
   asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
@@ -266,68 +270,55 @@ __device__ __forceinline__ void st_release_sys(int* p, int v) {
   asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-__device__ __forceinline__ void grid_barrier(const PArgs& a) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    volatile unsigned* gen = a.bar + 1;
-    const unsigned g = *gen;
-    __threadfence();
-    if (atomicAdd(a.bar, 1u) == gridDim.x - 1) {
-      a.bar[0] = 0;
-      __threadfence();
-      atomicAdd(a.bar + 1, 1u);
-    } else {
-      const long long t0 = clock64();
-      while (*gen == g) {
-        if (clock64() - t0 > a.timeout) {
-          *a.error = 1;
-          break;
-        }
-      }
-    }
-    __threadfence();
-  }
-  __syncthreads();
-}
-
 __global__ void __launch_bounds__(GG_THREADS, 2) greb_grid_persistent_kernel(const PArgs a) {
   extern __shared__ float sm[];
+  __shared__ int next_item;
   GridArgs g = a.g;
-  for (int n = 0; n < a.nsub; ++n) {
-    const int L = a.level0 + n;
-    for (int it = blockIdx.x; it < a.nitems; it += gridDim.x) {
-      const int code = a.order[it];
-      const PField& f = a.f[code >> 16];
-      const int k = code & 0xffff;
-      const int side = (k < a.k0 + 2) ? 0 : (k >= a.k1 - 2 ? 1 : -1);
-      float* peer = nullptr;
-      if (side >= 0 && f.nbX[side][0]) {
-        if (threadIdx.x == 0) {   // the neighbour's rows of level L must have landed in my halo
-          const long long t0 = clock64();
-          while (ld_acquire_sys(f.myflags + side * 2) < L || ld_acquire_sys(f.myflags + side * 2 + 1) < L) {
-            if (clock64() - t0 > a.timeout) {
-              *a.error = 1;
-              break;
-            }
+  const int total = a.nsub * a.nitems;             // < 2^31 (checked by the host)
+  int item = blockIdx.x;                           // the first gridDim.x items are taken statically
+  while (item < total) {
+    const int n = item / a.nitems, L = a.level0 + n;
+    const int code = a.order[item - n * a.nitems];
+    const PField& f = a.f[code >> 16];
+    const int k = code & 0xffff;
+    int fetched = 0;
+    if (threadIdx.x == 0) fetched = (int)atomicAdd(a.counter, 1u);   // the next item: in flight during this one
+    // dependencies: rows k-2 .. k+2 at level >= L (threads 0..4 poll one counter each)
+#ifndef GG_DBG_NOWAIT   // timing experiment only (wrong results): no dependency waits
+    if (threadIdx.x < 5) {
+      const int kk = k - 2 + (int)threadIdx.x;
+      if (kk >= 0 && kk < a.g.ny) {   // incl. row k itself: its level-L values come from another CTA's item
+        const long long t0 = clock64();
+        // relaxed polling (L2): what makes the row's VALUES visible is the producer's fence before its release
+        // store plus the fact that the field is read with ld.global.cg (L2), never from this SM's L1
+        while (*reinterpret_cast<const volatile int*>(f.level + kk) < L) {
+          if (clock64() - t0 > a.timeout) {
+            *a.error = 1;
+            break;
           }
         }
-        peer = f.nbX[side][(L + 1) & 1];
-      }
-      __syncthreads();            // flag seen by thread 0 -> everybody; also: the previous item's smem is free
-      g.X = f.X[L & 1];
-      g.Xnew = f.Xw[(L + 1) & 1];
-      g.wz = f.wz;
-      g.u = f.u;
-      g.v = f.v;
-      grid_row_substep(g, k, sm, peer);
-      if (peer) {
-        __threadfence_system();   // my stores into the neighbour's memory are visible system-wide ...
-        __syncthreads();
-        if (threadIdx.x == 0)     // ... before the flag that announces them
-          st_release_sys(f.nbflags[side] + (side == 0 ? k - a.k0 : k - (a.k1 - 2)), L + 1);
       }
     }
-    grid_barrier(a);
+#endif
+    __syncthreads();              // dependencies seen -> everybody; the previous item's shared memory is free
+    const int side = (k < a.k0 + 2) ? 0 : (k >= a.k1 - 2 ? 1 : -1);
+    float* peer = (side >= 0) ? f.nbX[side][(L + 1) & 1] : nullptr;
+    g.X = f.X[L & 1];
+    g.Xnew = f.Xw[(L + 1) & 1];
+    g.wz = f.wz;
+    g.u = f.u;
+    g.v = f.v;
+    grid_row_substep(g, k, sm, peer);
+    __syncthreads();              // every thread's stores of the new row precede thread 0's fence (CTA scope) ...
+    if (threadIdx.x == 0) {
+      if (peer) __threadfence_system();   // ... which makes them visible GPU- / system-wide (cumulativity) ...
+      else __threadfence();
+      st_release_sys(f.level + k, L + 1);  // ... before the row's level counter
+      if (peer) st_release_sys(f.nblevel[side] + k, L + 1);
+      next_item = fetched;
+    }
+    __syncthreads();
+    item = (int)gridDim.x + next_item;
   }
 }
 
@@ -349,13 +340,15 @@ struct greb_grid_handle_s {
   int last_launches = 0;
   bool pending = false;  // an asynchronous batch whose elapsed time has not been read yet
   // persistent path
-  int* d_flags = nullptr;      // [0..3] halo flags written by the neighbours ([side][row]), [4] error word
-  unsigned* d_bar = nullptr;   // grid barrier (leader handle of a group)
+  int* d_level = nullptr;      // [nrows] level of every stored row (halo rows: written by the neighbours)
+  bool level_stale = false;    // the launch-per-sub-step path advanced the band since d_level was written
+  int* d_flags = nullptr;      // [4] error word
+  unsigned* d_bar = nullptr;   // [0] work counter (leader handle of a group)
   int* d_order = nullptr;      // work-item order (leader handle)
   int order_items = 0, order_fields = 0;
   int level = 0;               // sub-steps done since set_fields
   float* nbX[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // neighbour buffers opened through CUDA IPC
-  int* nbflags[2] = {nullptr, nullptr};
+  int* nblevel[2] = {nullptr, nullptr};
   int nb_kbase[2] = {0, 0};
   std::string err;
 };
@@ -417,6 +410,8 @@ extern "C" int greb_grid_create(greb_grid_t* out, int nx, int ny, int k0, int k1
   for (int** p : ip) ok = ok && cudaMalloc((void**)p, (size_t)ny * sizeof(int)) == cudaSuccess;
   ok = ok && cudaMalloc((void**)&h->d_flags, 16 * sizeof(int)) == cudaSuccess &&
        cudaMemset(h->d_flags, 0, 16 * sizeof(int)) == cudaSuccess;
+  ok = ok && cudaMalloc((void**)&h->d_level, (size_t)h->nrows * sizeof(int)) == cudaSuccess &&
+       cudaMemset(h->d_level, 0, (size_t)h->nrows * sizeof(int)) == cudaSuccess;
   ok = ok && cudaMalloc((void**)&h->d_bar, 4 * sizeof(unsigned)) == cudaSuccess &&
        cudaMemset(h->d_bar, 0, 4 * sizeof(unsigned)) == cudaSuccess;
   if (!ok) {
@@ -435,10 +430,10 @@ extern "C" int greb_grid_destroy(greb_grid_t h) {
   for (int sd = 0; sd < 2; ++sd) {
     for (int b = 0; b < 2; ++b)
       if (h->nbX[sd][b]) cudaIpcCloseMemHandle(h->nbX[sd][b]);
-    if (h->nbflags[sd]) cudaIpcCloseMemHandle(h->nbflags[sd]);
+    if (h->nblevel[sd]) cudaIpcCloseMemHandle(h->nblevel[sd]);
   }
   void* ptrs[] = {h->d_X[0], h->d_X[1], h->d_wz, h->d_u, h->d_v, h->d_ccx_diff, h->d_ccx_adv, h->d_ccx2_diff,
-                  h->d_ccx2_adv, h->d_polar, h->d_t2d, h->d_t2a, h->d_flags, h->d_bar, h->d_order};
+                  h->d_ccx2_adv, h->d_polar, h->d_t2d, h->d_t2a, h->d_flags, h->d_bar, h->d_order, h->d_level};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -515,6 +510,8 @@ extern "C" int greb_grid_set_fields(greb_grid_t h, const float* X, const float* 
   GCK(cudaMemcpy(h->d_u, u + off, fb, cudaMemcpyHostToDevice));
   GCK(cudaMemcpy(h->d_v, v + off, fb, cudaMemcpyHostToDevice));
   GCK(cudaMemset(h->d_flags, 0, 16 * sizeof(int)));
+  GCK(cudaMemset(h->d_level, 0, (size_t)h->nrows * sizeof(int)));
+  h->level_stale = false;
   h->cur = 0;
   h->level = 0;
   h->valid_lo = h->kbase;
@@ -587,6 +584,7 @@ extern "C" int greb_grid_substeps_async(greb_grid_t h, int n) {
     h->last_launches++;
     h->cur ^= 1;
     h->level++;          // invariant: the current level lives in d_X[level & 1] (the persistent path relies on it)
+    h->level_stale = true;
     h->valid_lo = lo;
     h->valid_hi = hi;
   }
@@ -611,7 +609,7 @@ extern "C" int greb_grid_ipc_export(greb_grid_t h, void* out) {
   memset(&b, 0, sizeof b);
   GCK(cudaIpcGetMemHandle(&b.X[0], h->d_X[0]));
   GCK(cudaIpcGetMemHandle(&b.X[1], h->d_X[1]));
-  GCK(cudaIpcGetMemHandle(&b.flags, h->d_flags));
+  GCK(cudaIpcGetMemHandle(&b.flags, h->d_level));
   b.kbase = h->kbase;
   b.nrows = h->nrows;
   b.nx = h->nx;
@@ -638,7 +636,7 @@ extern "C" int greb_grid_ipc_import(greb_grid_t h, int side, const void* in) {
   }
   void* p = nullptr;
   GCK(cudaIpcOpenMemHandle(&p, b.flags, cudaIpcMemLazyEnablePeerAccess));
-  h->nbflags[side] = (int*)p;
+  h->nblevel[side] = (int*)p;
   h->nb_kbase[side] = b.kbase;
   return 0;
 }
@@ -656,7 +654,8 @@ extern "C" int greb_grid_run_persistent(greb_grid_t* hs, int nfields, int n) {
     if ((g->k0 > 0 && (g->halo < 2 || !g->nbX[0][0])) || (g->k1 < g->ny && (g->halo < 2 || !g->nbX[1][0])))
       return gfail(h, "greb_grid_run_persistent: an inner band needs halo_rows >= 2 and both neighbours imported");
   }
-  if (n < 0) return gfail(h, "greb_grid_run_persistent: n < 0");
+  if (n < 0 || (long long)n * nfields * (h->k1 - h->k0) > 2000000000LL)
+    return gfail(h, "greb_grid_run_persistent: n < 0 or more than 2e9 work items in one call");
   if (h->k1 - h->k0 < 4 && (h->k0 > 0 || h->k1 < h->ny)) return gfail(h, "greb_grid_run_persistent: bands need >= 4 rows");
   cudaSetDevice(h->device);
   if (h->pending) {
@@ -715,16 +714,21 @@ extern "C" int greb_grid_run_persistent(greb_grid_t* hs, int nfields, int n) {
     a.f[f].wz = g->d_wz + shift;
     a.f[f].u = g->d_u + shift;
     a.f[f].v = g->d_v + shift;
+    if (g->level_stale) {   // the launch-per-sub-step path moved the band: every stored row is at g->level
+      std::vector<int> lv(g->nrows, g->level);
+      GCK(cudaMemcpy(g->d_level, lv.data(), lv.size() * sizeof(int), cudaMemcpyHostToDevice));
+      g->level_stale = false;
+    }
+    a.f[f].level = g->d_level - g->kbase;
     for (int sd = 0; sd < 2; ++sd) {
       if (!g->nbX[sd][0]) continue;
-      // the neighbour keeps level L in ITS buffer of the same parity rule: its cur/level evolve in lockstep
-      // with mine (same number of sub-steps since set_fields), and both start with level 0 in d_X[0]
+      // the neighbour keeps level L in ITS buffer L & 1 as well (same invariant, same number of sub-steps
+      // since set_fields)
       const ptrdiff_t nshift = -(ptrdiff_t)g->nb_kbase[sd] * g->nx;
       a.f[f].nbX[sd][0] = g->nbX[sd][0] + nshift;
       a.f[f].nbX[sd][1] = g->nbX[sd][1] + nshift;
-      a.f[f].nbflags[sd] = g->nbflags[sd] + (1 - sd) * 2;
+      a.f[f].nblevel[sd] = g->nblevel[sd] - g->nb_kbase[sd];
     }
-    a.f[f].myflags = g->d_flags;
   }
   a.nfields = nfields;
   a.k0 = h->k0;
@@ -733,7 +737,7 @@ extern "C" int greb_grid_run_persistent(greb_grid_t* hs, int nfields, int n) {
   a.nsub = n;
   a.nitems = h->order_items;
   a.order = h->d_order;
-  a.bar = h->d_bar;
+  a.counter = h->d_bar;
   a.error = h->d_flags + 4;
   a.timeout = 6000000000LL;   // ~3 s at 2 GHz: a rank that never arrives ends the kernel instead of hanging the GPU
   const size_t smem = (size_t)4 * (h->nx + 6) * sizeof(float);
@@ -741,7 +745,11 @@ extern "C" int greb_grid_run_persistent(greb_grid_t* hs, int nfields, int n) {
   GCK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, greb_grid_persistent_kernel, GG_THREADS, smem));
   GCK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
   int grid = per_sm * sms;
-  if (grid > a.nitems) grid = a.nitems;
+  if ((long long)grid > (long long)a.nitems * n) grid = a.nitems * n;
+  if (getenv("GREB_GRID_DEBUG"))
+    fprintf(stderr, "greb_grid_run_persistent: %d CTAs/SM x %d SMs, grid %d, %d items per level, %d levels\n", per_sm, sms,
+            grid, a.nitems, n);
+  if (n == 0) return 0;
   if (grid < 1) return gfail(h, "greb_grid_run_persistent: the kernel does not fit an SM");
   GCK(cudaMemsetAsync(h->d_bar, 0, 4 * sizeof(unsigned), h->stream));
   void* params[] = {&a};

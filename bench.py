@@ -99,6 +99,13 @@ def parity_margins():
 WORKLOAD = "configs[2]: 1024-member perturbed-parameter/CO2 ensemble per GPU, 96x48, synthetic S0 forcing"
 
 
+def workload_config(members_per_gpu: int, shared_physics: bool = False) -> dict:
+    """the `config` both arms print, key for key: what is computed, not how"""
+    return {"workload": WORKLOAD, "members_per_gpu": members_per_gpu, "grid": "96x48",
+            "step": "one simulated year (730 steps, 12 month-end outputs x 5 fields) for every member",
+            "physics": "shared (CO2-only)" if shared_physics else "perturbed per member (campaign.perturbed_member)"}
+
+
 def member_physics(m: int, default_physics=None):
     """SURVEY.md 8d config 3 draws (greb_b200/campaign.py)."""
     from greb_b200 import campaign
@@ -176,9 +183,11 @@ def cpu_baseline(years: int, forcing=None, cores: int | None = None) -> dict:
         procs = []
         for c in range(cores):
             nml = os.path.join(tmp, f"nml_{c}")
+            p, co2 = member_physics(c)            # core c integrates member c of the same perturbed ensemble
+            phys = "".join(f"{k} = {getattr(p, k)!r}\n" for k in ("kappa", "ct_sens", "ce", "co_turb", "a_cloud", "da_ice"))
             with open(nml, "w") as fh:
-                fh.write("&PHYSICS_PAR\n/\n&NUMERICS_PAR\ntime_flux = 0\ntime_scnr = %d\n/\n&DIAGNOSTICS_PAR\n"
-                         "ens_id = \"%d\"\n/\n&CO2_PAR\nco2_ppm = 680\n/\n" % (years, c))
+                fh.write("&PHYSICS_PAR\n%s/\n&NUMERICS_PAR\ntime_flux = 0\ntime_scnr = %d\n/\n&DIAGNOSTICS_PAR\n"
+                         "ens_id = \"%d\"\n/\n&CO2_PAR\nco2_ppm = %r\n/\n" % (phys, years, c, co2))
         t0 = time.perf_counter()
         for c in range(cores):
             cmd = [om.CLI, os.path.join(tmp, f"nml_{c}"), "--no-output", "--time"]
@@ -197,8 +206,8 @@ def cpu_baseline(years: int, forcing=None, cores: int | None = None) -> dict:
         # throughput of the scenario phase with all cores busy (slowest process bounds the job)
         value = cores * years / max(scen)
         return {"value": value, "unit": "member-years/s", "cores": cores, "kind": "port",
-                "sample": f"{cores} oracle processes (one per core, taskset), {years} scenario years each at 680 ppm, "
-                          f"default physics, S0 forcing; wall {wall:.1f}s incl. input read",
+                "sample": f"{cores} oracle processes (one per core, taskset), {years} scenario years each, members "
+                          f"0..{cores - 1} of the same perturbed ensemble, S0 forcing; wall {wall:.1f}s incl. input read",
                 "note": "C restatement of src/greb.f90 built -O3 -ffp-contract=off (no Fortran compiler in the image)"}
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
@@ -218,8 +227,10 @@ def run_reference(args, rank: int, world: int):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1000.0 * cores / cb["value"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "reference_arm": "oracle port of src/greb.f90, one process per host core",
-                   "step": "one simulated year per core"},
+        "config": workload_config(args.members, args.shared_physics),
+        "arm": {"reference_arm": "oracle port of src/greb.f90 (the reference's CPU path), one process per host core, "
+                                 "each integrating one member of the ensemble for `steps` simulated years",
+                "arithmetic": "IEEE fp32 in the reference's operation order, glibc libm (gcc -O3 -ffp-contract=off)"},
         "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": cb["value"], "unit": "member-years/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": wall,
@@ -428,19 +439,17 @@ def main():
             "metric": "member-years/sec", "value": value, "unit": "member-years/s", "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": ev_ms_max / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "members_per_gpu": M, "grid": "96x48",
-                       "step": "one simulated year (730 steps, 12 month-end outputs x 5 fields) for every member",
-                       "physics": "shared (CO2-only)" if args.shared_physics else "perturbed per member",
-                       "l2": "inputs larger than L2 (per-member flux corrections 40 MB x members)",
-                       "waves": f"{M} members on 148 SMs = {M / 148:.2f} waves of one CTA per SM "
-                                f"({(1 - M / (148 * -(-M // 148))) * 100:.1f} % of the last wave idle)",
-                       "arithmetic": ("fast mode (GREB_ARITH_FAST: factored stencils, FMA contraction, approximate "
-                                      "division/log/exp in the column physics; config 1 and 2 and 14 of 16 perturbed "
-                                      "members within 1.5e-3 K over 50 years, 2 low-CO2 members outside the 0.01 K gate)"
-                                      if args.arith == "fast" else
-                                      "exact mode (the reference's IEEE operation order, no FMA contraction, IEEE "
-                                      "divisions, glibc's expf/logf restated on the device: 16 perturbed members x "
-                                      "(3+50) years bit-identical to the oracle, tests/test_gpu_long_parity.py)")},
+            "config": workload_config(M, args.shared_physics),
+            "arm": {"l2": "inputs larger than L2 (per-member flux corrections 40 MB x members)",
+                    "waves": f"{M} members on 148 SMs = {M / 148:.2f} waves of one CTA per SM "
+                             f"({(1 - M / (148 * -(-M // 148))) * 100:.1f} % of the last wave idle)",
+                    "arithmetic": ("fast mode (GREB_ARITH_FAST: factored stencils, FMA contraction, approximate "
+                                   "division/log/exp in the column physics; config 1 and 2 and 14 of 16 perturbed "
+                                   "members within 1.5e-3 K over 50 years, 2 low-CO2 members outside the 0.01 K gate)"
+                                   if args.arith == "fast" else
+                                   "exact mode (the reference's IEEE operation order, no FMA contraction, IEEE "
+                                   "divisions, glibc's expf/logf restated on the device: 16 perturbed members x "
+                                   "(3+50) years bit-identical to the oracle, tests/test_gpu_long_parity.py)")},
             "roofline": roofline,
             "e2e": e2e,
             "gpu_launches": launches,

@@ -32,7 +32,8 @@ def main():
     ap.add_argument("--time-scnr", type=int, default=50)
     ap.add_argument("--batch", type=int, default=2048,
                     help="members per handle (40.4 MB of corrections each); 0 = as many as fit the free device memory")
-    ap.add_argument("--arith", default="fast", choices=["fast", "exact"])
+    ap.add_argument("--arith", default="exact", choices=["fast", "exact"],
+                    help="exact (default): bit-identical to the reference arithmetic; fast: see DESIGN.md section 4")
     ap.add_argument("--out-stride", type=int, default=1024, help="members = 0 mod this keep their monthly fields")
     ap.add_argument("--save", default=None, help="npz file for rank 0's annual means and the ensemble statistics")
     args = ap.parse_args()

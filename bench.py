@@ -285,7 +285,7 @@ def main():
 
     M = args.members
     K, W = args.steps, max(args.warmup, 0)
-    n_years = W + K + 24      # warm-up + timed + e2e (1 + up to 6) + the other arithmetic mode (3) + slack
+    n_years = W + K + 30      # warm-up + timed + e2e (1 + up to 12) + the other arithmetic mode (3) + slack
     forcing = synth.cached_forcing(cache_dir=os.environ.get("GREB_FORCING_CACHE", "/tmp/greb_b200_cache"))
 
     ens = greb_b200.Ensemble(M, device=local)
@@ -375,15 +375,16 @@ def main():
         states = torch.empty((M, 5, 48, 96), dtype=torch.float32).pin_memory()
         monthly = [torch.empty((M, 1, 12, 5, 48, 96), dtype=torch.float32).pin_memory() for _ in range(2)]
         ens.get_states(ptr=states.data_ptr())
-        ne = max(3, min(K, 6))
+        ne = max(3, min(K, 12))
         for i in range(1 + ne):
             if i == 1:
                 ens.wait()
                 sync_all()
                 te = time.perf_counter()
             ens.set_states_async(states.data_ptr())                     # H2D: every member's state
-            ens.run_async(1, monthly[i & 1].data_ptr())                 # kernel; records -> pinned buffer (copy stream)
-            ens.get_states_async(states.data_ptr())                     # D2H: end state (next step's input)
+            ens.run_async(1)                                            # the year's kernel
+            ens.get_states_async(states.data_ptr())                     # D2H: end state (next step's input) ...
+            ens.fetch_monthly_async(monthly[i & 1].data_ptr())          # ... ahead of the 1.1 GB of records (copy stream)
             ens.sync_compute()                                          # kernel + state copies done; records may still fly
             float(diag_allreduce()[0])                                  # D2H read of the step's diagnostic
         ens.wait()                                                      # the last year's records are on the host

@@ -784,6 +784,36 @@ extern "C" int greb_b200_run_async(greb_b200_t h, int years, float* out, const i
   return GREB_OK;
 }
 
+// The last completed year's records -> host, on the copy stream, ordered behind everything enqueued on the
+// compute stream SO FAR (so a small state transfer issued before this call is not stuck behind 1 GB of
+// records on the same DMA engine).  Completed by greb_b200_wait.
+extern "C" int greb_b200_fetch_monthly_async(greb_b200_t h, float* out, const int* out_members, int n_out) {
+  if (!h) return GREB_E_INVALID;
+  if (!h->inited || !out) return fail(h, GREB_E_INVALID, "greb_b200_fetch_monthly_async: bad arguments");
+  const int N = h->n_members;
+  if (!out_members) n_out = N;
+  if (out_members)
+    for (int i = 0; i < n_out; ++i)
+      if (out_members[i] < 0 || out_members[i] >= N)
+        return fail(h, GREB_E_INVALID, "greb_b200_fetch_monthly_async: out_members entry out of range");
+  cudaSetDevice(h->device);
+  const int b = h->last_out;
+  const size_t year_floats = (size_t)12 * 5 * GNC;
+  CK(cudaEventRecord(h->ev_k[b], h->stream));
+  CK(cudaStreamWaitEvent(h->copy_stream, h->ev_k[b], 0));
+  if (!out_members) {
+    CK(cudaMemcpyAsync(out, h->d_out[b], (size_t)N * year_floats * 4, cudaMemcpyDeviceToHost, h->copy_stream));
+  } else {
+    for (int i = 0; i < n_out; ++i)
+      CK(cudaMemcpyAsync(out + (size_t)i * year_floats, h->d_out[b] + (size_t)out_members[i] * year_floats,
+                         year_floats * 4, cudaMemcpyDeviceToHost, h->copy_stream));
+  }
+  CK(cudaEventRecord(h->ev_c[b], h->copy_stream));
+  h->copy_pending[b] = true;
+  h->pending = true;   // greb_b200_wait (or any other entry point) drains the copy stream
+  return GREB_OK;
+}
+
 extern "C" int greb_b200_run(greb_b200_t h, int years, float* out, const int* out_members, int n_out, float* gmean,
                              float* gmean_coslat) {
   if (!h) return GREB_E_INVALID;

@@ -31,7 +31,8 @@ ABI_SYMBOLS = ["greb_b200_physics_defaults", "greb_b200_physics_original", "greb
                "greb_b200_run_async", "greb_b200_wait", "greb_b200_time_steps", "greb_b200_set_states_async",
                "greb_b200_get_states_async", "greb_b200_sync_compute", "greb_b200_get_calendar",
                "greb_b200_set_calendar", "greb_b200_get_accumulators", "greb_b200_set_accumulators",
-               "greb_b200_device_libm", "greb_b200_ensemble_moments", "greb_b200_ensemble_moments_device"]
+               "greb_b200_device_libm", "greb_b200_ensemble_moments", "greb_b200_ensemble_moments_device",
+               "greb_b200_fetch_monthly_async"]
 
 
 class Physics(C.Structure):
@@ -99,6 +100,7 @@ def load_library():
     L.greb_b200_run.argtypes = [vp, C.c_int, vp, ip, C.c_int, fp, fp]
     L.greb_b200_run_async.argtypes = [vp, C.c_int, vp, ip, C.c_int, fp, fp]
     L.greb_b200_wait.argtypes = [vp]
+    L.greb_b200_fetch_monthly_async.argtypes = [vp, vp, ip, C.c_int]
     L.greb_b200_time_loop.argtypes = [vp, C.c_int]
     L.greb_b200_time_steps.argtypes = [vp, C.c_int, C.c_int]
     L.greb_b200_set_states_async.argtypes = [vp, vp]
@@ -256,6 +258,12 @@ class Ensemble:
         self._ck(rc, "greb_b200_run_async")
         self._keep_om = om
         self.years_run += years
+
+    def fetch_monthly_async(self, out_ptr: int):
+        """records of the last completed year of ALL members -> host address `out_ptr` (pinned), behind what
+        the compute stream holds now; wait() completes it"""
+        self._ck(self.L.greb_b200_fetch_monthly_async(self.h, C.c_void_p(out_ptr), None, self.n),
+                 "greb_b200_fetch_monthly_async")
 
     def wait(self):
         self._ck(self.L.greb_b200_wait(self.h), "greb_b200_wait")

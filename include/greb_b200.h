@@ -163,6 +163,10 @@ int greb_b200_run(greb_b200_t h, int years, float* out, const int* out_members, 
 int greb_b200_run_async(greb_b200_t h, int years, float* out, const int* out_members, int n_out, float* gmean,
                         float* gmean_coslat);
 int greb_b200_wait(greb_b200_t h);
+/* The last completed year's records -> host (pinned) on the copy stream, ordered behind whatever is enqueued
+ * on the compute stream at the time of the call; completed by greb_b200_wait.  With run_async(out = NULL)
+ * it lets a host put a small transfer (the end state) ahead of the gigabyte of records on the DMA engine. */
+int greb_b200_fetch_monthly_async(greb_b200_t h, float* out, const int* out_members, int n_out);
 
 /* One time_loop call (src/greb.f90:239-274) for every member with step counter `it` (1-based,
  * as the reference's `it`).  Test entry: lets a host drive the loop step by step.

@@ -109,6 +109,21 @@ def test_run_async_chained_equals_run(forcing):
     for y in range(3):
         assert np.array_equal(bufs[y].numpy()[:, 0], want[:, y]), y
     assert np.array_equal(b.get_states(), end)
+    # run_async without records + fetch_monthly_async behind a state transfer (the bench's e2e pipeline)
+    c = make_ensemble(forcing, ps, co2)
+    c.spinup(1)
+    c.reset_scenario()
+    st = torch.empty((3, 5, 48, 96), dtype=torch.float32).pin_memory()
+    for y in range(3):
+        c.run_async(1)
+        c.get_states_async(st.data_ptr())
+        c.fetch_monthly_async(bufs[y].data_ptr())
+        c.sync_compute()
+    c.wait()
+    for y in range(3):
+        assert np.array_equal(bufs[y].numpy()[:, 0], want[:, y]), y
+    assert np.array_equal(st.numpy(), end)
+    c.close()
     it = b.get_calendar()
     with pytest.raises(greb_b200.GrebError):
         b.run(1, out_members=[0, 7])                     # bad member index: nothing may have been launched

@@ -367,26 +367,30 @@ def main():
     # ---- end to end through the C ABI with host buffers -------------------------------------
     # Every step: H2D of every member's state from pinned memory, one simulated year, D2H of the end state and
     # of the year's diagnostic (read on the host: the step's "loss"), D2H of all 12 x 5 monthly-mean records.
-    # The records of year y are copied by the library's copy stream while year y+1 runs (greb_b200_run_async,
-    # two pinned record buffers); the timed region ends with greb_b200_wait, i.e. when the LAST year's
-    # records have landed.
+    # The records of year y are copied by the library's copy stream while year y+1 runs (greb_b200_run_async +
+    # greb_b200_fetch_monthly_async, two pinned record buffers) and are queued BEHIND the next step's state
+    # upload: a saturated D2H stream would otherwise throttle that upload (PCIe read requests travel upstream)
+    # and with it the start of the next kernel.  The timed region ends with greb_b200_wait, i.e. when the LAST
+    # year's records have landed.
     e2e = None
     if not args.no_e2e:
         states = torch.empty((M, 5, 48, 96), dtype=torch.float32).pin_memory()
         monthly = [torch.empty((M, 1, 12, 5, 48, 96), dtype=torch.float32).pin_memory() for _ in range(2)]
         ens.get_states(ptr=states.data_ptr())
         ne = max(3, min(K, 12))
+        ens.set_states_async(states.data_ptr())                         # the first step's input (untimed iteration 0)
         for i in range(1 + ne):
             if i == 1:
                 ens.wait()
                 sync_all()
                 te = time.perf_counter()
-            ens.set_states_async(states.data_ptr())                     # H2D: every member's state
             ens.run_async(1)                                            # the year's kernel
-            ens.get_states_async(states.data_ptr())                     # D2H: end state (next step's input) ...
-            ens.fetch_monthly_async(monthly[i & 1].data_ptr())          # ... ahead of the 1.1 GB of records (copy stream)
-            ens.sync_compute()                                          # kernel + state copies done; records may still fly
+            ens.get_states_async(states.data_ptr())                     # D2H: end state (the host's copy of the result)
+            ens.sync_compute()                                          # kernel + end state done
             float(diag_allreduce()[0])                                  # D2H read of the step's diagnostic
+            ens.set_states_async(states.data_ptr())                     # H2D: the next step's input state ...
+            ens.fetch_monthly_async(monthly[i & 1].data_ptr())          # ... then the 1.1 GB of records: the copy stream
+            #                                                             starts behind the H2D and runs under the next kernel
         ens.wait()                                                      # the last year's records are on the host
         sync_all()
         dt = time.perf_counter() - te

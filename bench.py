@@ -269,6 +269,13 @@ def main():
         run_reference(args, rank, world)
         return
 
+    # The contract is ONE JSON line on stdout.  Native libraries write there too (NCCL prints its version
+    # banner on file descriptor 1 whatever NCCL_DEBUG says), so descriptor 1 is pointed at stderr for the
+    # whole run and the JSON line goes to a private duplicate of the real stdout.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
     import greb_b200
@@ -527,7 +534,7 @@ def main():
         if world == 1 and not args.no_cpu_baseline and not args.quick:
             cb = cpu_baseline(years=6, forcing=forcing)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        print(json.dumps(line), flush=True)
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
 
     if getattr(ens, "h", None):
         ens.close()

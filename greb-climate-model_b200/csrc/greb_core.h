@@ -363,6 +363,58 @@ GDEV void substep_y(Tile& t, const vf (&dTx)[GREB_CPT], const vf (&aTx)[GREB_CPT
   }
 }
 
+// The same y part on PAIRS of adjacent cells (exact mode, rows without the special advection formula;
+// build option GREB_PACKED_Y, greb_types.h): every add, subtract, multiply and fused multiply-add is one
+// packed instruction for two cells (FADD2 / FMUL2 / FFMA2, greb_simt.h) — the IEEE operation on each half, so
+// the results are the scalar code's bit for bit.  The y part has no coupling along the row, and LDS.128
+// delivers two ready-made pairs, so no data is permuted; only the wind-branch selections stay scalar.
+GDEV vf2 p_div3(vf2 x) {
+#if GREB_DEVICE
+  const vf2 r = p_bcast(0.3333333432674407958984375f);
+  const vf2 q = p_mul(x, r);
+  const vf2 e = p_fma(p_bcast(-3.0f), q, x);
+  return p_fma(e, r, q);
+#else
+  return p_pack(div3(p_lo(x)), div3(p_hi(x)));
+#endif
+}
+GDEV void substep_y_packed(Tile& t, const vf (&dTx)[GREB_CPT], const vf (&aTx)[GREB_CPT], const RowGeom& g,
+                           const GrebMemberConst& mc, const float* buf, float* smem) {
+  const vf2 ccyd = p_bcast(mc.ccy_diff), ccya = p_bcast(mc.ccy_adv);
+  GUNROLL
+  for (int q = 0; q < 3; ++q) {
+    vf2 tm2[2], tm1[2], tp1[2], tp2[2], V[2], Wm1[2], Wp1[2], WFY[2];
+    p_ld2(V, priv_ptr(smem, PRIV_V, q), g.tid4);
+    p_ld2(Wm1, priv_ptr(smem, PRIV_WM1, q), g.tid4);
+    p_ld2(Wp1, priv_ptr(smem, PRIV_WP1, q), g.tid4);
+    p_ld2(WFY, priv_ptr(smem, PRIV_WFY, q), g.tid4);
+    p_ld2(tm1, buf, g.km1 * GX + g.col + 4 * q);
+    p_ld2(tp1, buf, g.kp1 * GX + g.col + 4 * q);
+    p_ld2(tm2, buf, g.km2 * GX + g.col + 4 * q);
+    p_ld2(tp2, buf, g.kp2 * GX + g.col + 4 * q);
+    GUNROLL
+    for (int h = 0; h < 2; ++h) {
+      const int j = 4 * q + 2 * h;
+      const vf2 T = p_pack(t.T[j], t.T[j + 1]);
+      const vf2 Pym1 = p_mul(Wm1[h], p_sub(T, tm1[h]));        // wz(k-1)*(T(k)-T(k-1))
+      const vf2 Qy0 = p_mul(Wp1[h], p_sub(tp1[h], T));         // wz(k+1)*(T(k+1)-T(k))
+      const vf2 dTy = p_mul(ccyd, p_sub(Qy0, Pym1));           // f:587-588
+      const vb pv0 = p_lo(V[h]) >= 0.0f, pv1 = p_hi(V[h]) >= 0.0f;
+      const vf2 NV = p_pack(-v_abs(p_lo(V[h])), -v_abs(p_hi(V[h])));
+      const vf2 near = p_pack(v_sel(pv0, p_lo(Pym1), -p_lo(Qy0)), v_sel(pv1, p_hi(Pym1), -p_hi(Qy0)));
+      const vf2 tfar = p_pack(v_sel(pv0, p_lo(tm2[h]), p_lo(tp2[h])), v_sel(pv1, p_hi(tm2[h]), p_hi(tp2[h])));
+      const vf2 far = p_mul(WFY[h], p_sub(T, tfar));
+      const vf2 Xv = p_mul(NV, p_add(near, far));              // (-|v|)*(near+far), f:771-780
+      const vf2 aTy = p_div3(p_mul(ccya, Xv));
+      const vf2 dXd = p_mul(p_pack(t.W[j], t.W[j + 1]), p_add(p_pack(dTx[j], dTx[j + 1]), dTy));   // f:721
+      const vf2 dXa = p_add(p_pack(aTx[j], aTx[j + 1]), aTy);                                       // f:913
+      const vf2 Tn = p_add(p_add(T, dXd), dXa);                                                     // f:549
+      t.T[j] = p_lo(Tn);
+      t.T[j + 1] = p_hi(Tn);
+    }
+  }
+}
+
 // =============================================================================================
 //   FAST arithmetic mode (GREB_ARITH_FAST): the same stencils, algebraically factored and with FMA
 //   contraction — NOT bit-identical to the reference, held to the north_star tolerances instead
@@ -799,7 +851,11 @@ GDEV void circulation_main(const SimtCtx& ctx, Tile& t, const RowGeom& g, const 
     GCLK(c_w, tc)
     const float* buf = ss.hb + (ss.phase & 1) * GNC;
     if (MODE == 1) substep_y_fast(t, dTx, aTx, g, fr, buf, ss.smem);
+#if GREB_PACKED_Y
+    else if (g.ykind == 0) substep_y_packed(t, dTx, aTx, g, mc, buf, ss.smem);
+#else
     else if (g.ykind == 0) substep_y<false>(t, dTx, aTx, g, mc, buf, ss.smem);
+#endif
     else substep_y<true>(t, dTx, aTx, g, mc, buf, ss.smem);
 #endif
     ss.phase++;

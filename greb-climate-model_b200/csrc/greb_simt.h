@@ -146,6 +146,33 @@ GDEV vf v_div_fast(vf a, vf b) { return __fdividef(a, b); }
 GDEV vf v_log_fast(vf a) { return __logf(a); }
 GDEV vf v_exp_fast(vf a) { return __expf(a); }
 GDEV vb v_any_true(vb p) { return __any_sync(0xffffffffu, p); }  // uniform result
+// ---- packed pairs of fp32 (Blackwell FADD2 / FMUL2 / FFMA2) ---------------------------------------
+// A vf2 holds two independent fp32 values in an aligned 64-bit register pair; add / sub / mul / fma issue
+// as ONE instruction for both halves (half the issue slots of the scalar forms; tools/microbench: twice
+// the scalar FADD/FMUL rate).  Every operation is the IEEE round-to-nearest operation on each half, so
+// packing never changes results — with one caveat: ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into
+// FFMA2 even with --fmad=false (the scalar forms are left alone; tools/microbench/packed_exact.cu).  A
+// multiply and an add whose flush-to-zero modes differ cannot be contracted, so the packed add/sub carry
+// .ftz: they differ from IEEE only when an operand or the result is subnormal (< 1.2e-38), which no
+// temperature, humidity or increment of the model is (the whole-run bit-identity tests watch over it).
+struct vf2 { unsigned long long v; };
+GDEV vf2 p_pack(vf lo, vf hi) { vf2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi)); return r; }
+GDEV vf p_lo(vf2 a) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v)); return lo; }
+GDEV vf p_hi(vf2 a) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v)); return hi; }
+GDEV vf2 p_bcast(float x) { return p_pack(x, x); }
+GDEV vf2 p_add(vf2 a, vf2 b) { vf2 r; asm("add.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+GDEV vf2 p_sub(vf2 a, vf2 b) { vf2 r; asm("sub.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+GDEV vf2 p_mul(vf2 a, vf2 b) { vf2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+GDEV vf2 p_fma(vf2 a, vf2 b, vf2 c) {
+  vf2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+  return r;
+}
+// 4 consecutive floats = 2 packed pairs, 16-byte aligned (LDS.128)
+GDEV void p_ld2(vf2 (&o)[2], const float* p, vi idx) {
+  const ulonglong2 t = *reinterpret_cast<const ulonglong2*>(p + idx);
+  o[0].v = t.x; o[1].v = t.y;
+}
 // 4 consecutive floats, 16-byte aligned (LDG.128 / LDS.128 / STG.128 / STS.128)
 GDEV void v_ld4(vf (&o)[4], const float* p, vi idx) {
   const float4 t = *reinterpret_cast<const float4*>(p + idx);
@@ -355,6 +382,23 @@ GDEV void sb_wait(const SimtCtx&, SplitBar* b, int phase) {
 GDEV void flag_set(const SimtCtx&, int* f, int v) { __atomic_store_n(f, v, __ATOMIC_RELEASE); }
 GDEV void flag_wait(const SimtCtx&, const int* f, int v) {
   while (__atomic_load_n(f, __ATOMIC_ACQUIRE) != v) sched_yield();
+}
+
+// packed pairs: two lane vectors, every operation applied to each half
+struct vf2 { vf lo, hi; };
+GDEV vf2 p_pack(vf lo, vf hi) { vf2 r; r.lo = lo; r.hi = hi; return r; }
+GDEV vf p_lo(vf2 a) { return a.lo; }
+GDEV vf p_hi(vf2 a) { return a.hi; }
+GDEV vf2 p_bcast(float x) { return p_pack(vf(x), vf(x)); }
+GDEV vf2 p_add(vf2 a, vf2 b) { return p_pack(v_add(a.lo, b.lo), v_add(a.hi, b.hi)); }
+GDEV vf2 p_sub(vf2 a, vf2 b) { return p_pack(v_sub(a.lo, b.lo), v_sub(a.hi, b.hi)); }
+GDEV vf2 p_mul(vf2 a, vf2 b) { return p_pack(v_mul(a.lo, b.lo), v_mul(a.hi, b.hi)); }
+GDEV vf2 p_fma(vf2 a, vf2 b, vf2 c) { return p_pack(v_fma(a.lo, b.lo, c.lo), v_fma(a.hi, b.hi, c.hi)); }
+GDEV void p_ld2(vf2 (&o)[2], const float* p, vi idx) {
+  vf t[4];
+  v_ld4(t, p, idx);
+  o[0] = p_pack(t[0], t[1]);
+  o[1] = p_pack(t[2], t[3]);
 }
 
 // bulk copy stand-ins: the copy happens at issue time; the CTA barriers between issue and use order it

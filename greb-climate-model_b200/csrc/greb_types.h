@@ -26,6 +26,17 @@
 // part of a sub-step AFTER the barrier instead of before it, so that the shared-memory-bound y parts of
 // one half of the warps overlap the arithmetic-bound x parts of the other half (after a barrier all warps
 // used to hit the LDS pipe at once).  Same arithmetic, same results.
+// GREB_PACKED_Y (exact mode): the y part of a sub-step on pairs of cells with FADD2/FMUL2/FFMA2
+// (greb_core.h substep_y_packed): same IEEE operations — 16 perturbed members x 53 years stay bit-identical
+// on the B200 — and 20 % fewer issued instructions per sub-step (114 packed instructions replace 228), yet
+// the throughput does not move: 1,653.9 vs 1,654.2 member-years/s.  The circulation is bound by the
+// latency of each warp's dependent chain (SHFL -> stencil -> barrier -> LDS -> update) at 3.5 warps per
+// scheduler, not by issue slots.  Off by default (no gain, and .ftz on the packed adds); kept as a build
+// option and as evidence.  A variant that kept the wind branch in a bit mask register instead of
+// re-deriving it from V cost 5.5 % — one more live register at the 128-register limit spills in the loop.
+#ifndef GREB_PACKED_Y
+#define GREB_PACKED_Y 0
+#endif
 // GREB_YCOEF (fast arithmetic mode only): the latitudinal coefficients of a step are folded into three
 // per-cell factors CA, CB, CF once per step (instead of V, wz(k-1), wz(k+1), WFY), and the x part hands
 // over one array wz*dTx + aTx instead of two.

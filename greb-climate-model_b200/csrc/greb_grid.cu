@@ -261,32 +261,26 @@ struct PArgs {
   long long timeout;        // cycles
 };
 
-__device__ __forceinline__ int ld_acquire_sys(const int* p) {
-  int v;
-  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_sys(int* p, int v) {
-  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
 __global__ void __launch_bounds__(GG_THREADS, 2) greb_grid_persistent_kernel(const PArgs a) {
   extern __shared__ float sm[];
   __shared__ int next_item;
   GridArgs g = a.g;
   const int total = a.nsub * a.nitems;             // < 2^31 (checked by the host)
   int item = blockIdx.x;                           // the first gridDim.x items are taken statically
+  // Roles: warp 1 fetches the next item and polls the dependencies, thread 0 publishes the finished row.  The
+  // publication (fence + release stores, ~1 us) of item i runs beside warp 1's polling for item i+1 — the
+  // other 22 warps only ever wait at the two barriers that the data flow itself needs.
   while (item < total) {
     const int n = item / a.nitems, L = a.level0 + n;
     const int code = a.order[item - n * a.nitems];
     const PField& f = a.f[code >> 16];
     const int k = code & 0xffff;
     int fetched = 0;
-    if (threadIdx.x == 0) fetched = (int)atomicAdd(a.counter, 1u);   // the next item: in flight during this one
-    // dependencies: rows k-2 .. k+2 at level >= L (threads 0..4 poll one counter each)
+    if (threadIdx.x == 32) fetched = (int)atomicAdd(a.counter, 1u);   // the next item: in flight during this one
 #ifndef GG_DBG_NOWAIT   // timing experiment only (wrong results): no dependency waits
-    if (threadIdx.x < 5) {
-      const int kk = k - 2 + (int)threadIdx.x;
+    // dependencies: rows k-2 .. k+2 at level >= L (five lanes of warp 1 poll one counter each)
+    if (threadIdx.x >= 32 && threadIdx.x < 37) {
+      const int kk = k - 2 + (int)threadIdx.x - 32;
       if (kk >= 0 && kk < a.g.ny) {   // incl. row k itself: its level-L values come from another CTA's item
         const long long t0 = clock64();
         // relaxed polling (L2): what makes the row's VALUES visible is the producer's fence before its release
@@ -309,16 +303,18 @@ __global__ void __launch_bounds__(GG_THREADS, 2) greb_grid_persistent_kernel(con
     g.u = f.u;
     g.v = f.v;
     grid_row_substep(g, k, sm, peer);
+    if (threadIdx.x == 32) next_item = fetched;
     __syncthreads();              // every thread's stores of the new row precede thread 0's fence (CTA scope) ...
-    if (threadIdx.x == 0) {
-      if (peer) __threadfence_system();   // ... which makes them visible GPU- / system-wide (cumulativity) ...
-      else __threadfence();
-      st_release_sys(f.level + k, L + 1);  // ... before the row's level counter
-      if (peer) st_release_sys(f.nblevel[side] + k, L + 1);
-      next_item = fetched;
-    }
-    __syncthreads();
     item = (int)gridDim.x + next_item;
+    if (threadIdx.x == 0) {
+      // ... which makes them visible GPU-wide — system-wide only for the two rows that also went to the
+      // neighbour GPU (a system-scope fence costs microseconds) — before the row's level counter.  The
+      // counters themselves are plain volatile stores behind that fence.
+      if (peer) __threadfence_system();
+      else __threadfence();
+      *reinterpret_cast<volatile int*>(f.level + k) = L + 1;
+      if (peer) *reinterpret_cast<volatile int*>(f.nblevel[side] + k) = L + 1;
+    }
   }
 }
 

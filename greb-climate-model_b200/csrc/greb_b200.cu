@@ -109,6 +109,77 @@ __global__ void __launch_bounds__(GREB_NTHREADS, 1) greb_circulation_kernel(cons
   }
 }
 
+// Column physics of one 12-h step on TILES (BASELINE.json configs[4]: a whole step of one member on a grid of
+// any size).  SW/LW radiation, sensible heat, hydro, deep ocean, the Ts/To/cap_surf/Ta/q updates and sea ice
+// (f:277-308 + f:258-272) are cell-local, so a band of a big grid is cut into tiles of 4,608 consecutive cells
+// laid out exactly like an ensemble member ([tile][field][4608]); every tile carries its own slice of the
+// step's forcing, of the solar radiation (one value per 96-cell segment: 96 divides xdim) and of the flux
+// corrections.  One CTA per tile runs THE SAME device functions as the member kernel (column_phase_a/b/c), so
+// at 96x48 a step is bit-identical to it.  Phase 0 = A (before the circulations), 1 = B (after circulation of
+// Ta: X = the circulated field), 2 = C (after circulation of q).  The circulations themselves are greb_grid's.
+struct GrebTileArgs {
+  int phase, ntiles;
+  float co2;
+  const GrebMemberConst* mc;  // one physics for all tiles (device copy; group = 0, no switches)
+  const float* forc;          // [ntiles][GF_COUNT][GNC]
+  const float* sw_solar;      // [ntiles][GY]
+  const int* mask;            // [ntiles][GNC]
+  const float* z_ocean;       // [ntiles][GNC]
+  const float* wz;            // [ntiles][2][GNC]
+  float* corr;                // [ntiles][GC_COUNT][GNC]
+  float* state;               // [ntiles][GS_COUNT][GNC]
+  float* acc;                 // [ntiles][GA_COUNT][GNC]
+  float* stash;               // [ntiles][2][GNC]
+  const float* X;             // [ntiles][GNC] (phases 1, 2)
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(GREB_NMAIN * 32) greb_tile_phase_kernel(const GrebTileArgs ta) {
+  __shared__ GrebMemberConst mc_s;
+  {
+    const int* s = reinterpret_cast<const int*>(ta.mc);
+    int* d = reinterpret_cast<int*>(&mc_s);
+    for (int i = threadIdx.x; i < (int)(sizeof(GrebMemberConst) / sizeof(int)); i += blockDim.x) d[i] = s[i];
+  }
+  __syncthreads();
+  const int t = blockIdx.x;
+  GrebKernelArgs a;
+  a.forc = ta.forc + (size_t)t * GF_COUNT * GNC;
+  a.sw_solar = ta.sw_solar + (size_t)t * GY;
+  a.mask = ta.mask + (size_t)t * GNC;
+  a.z_ocean = ta.z_ocean + (size_t)t * GNC;
+  a.toclim = nullptr;
+  a.tclim = nullptr;
+  a.qclim = nullptr;
+  a.wz = ta.wz + (size_t)t * 2 * GNC;
+  a.corr = ta.corr + (size_t)t * GC_COUNT * GNC;
+  a.state = ta.state + (size_t)t * GS_COUNT * GNC;
+  a.acc = ta.acc + (size_t)t * GA_COUNT * GNC;
+  a.out = nullptr;
+  a.spinup = 0;
+  StepInfo si;
+  si.ityr = 0;
+  si.month_end = 0;
+  si.ndm = 1.0f;
+  si.out_rec = 0;
+  si.co2 = ta.co2;
+  si.spinup = 0;
+  float* stash = ta.stash + (size_t)t * 2 * GNC;
+  const int k = threadIdx.x >> 3, col = 12 * (threadIdx.x & 7);
+#pragma unroll 1
+  for (int q = 0; q < 3; ++q) {
+    const int idx0 = k * GX + col + 4 * q;
+    if (ta.phase == 0) {
+      column_phase_a<MODE, 0>(a, mc_s, 0, si, k, idx0, stash, a.corr);
+    } else {
+      const float4 x = *reinterpret_cast<const float4*>(ta.X + (size_t)t * GNC + idx0);
+      const float X4[4] = {x.x, x.y, x.z, x.w};
+      if (ta.phase == 1) column_phase_b(a, 0, si, idx0, X4, stash);
+      else column_phase_c(a, mc_s, 0, si, idx0, X4, stash, a.corr);
+    }
+  }
+}
+
 // Ensemble moments of the monthly-mean fields (SURVEY 8d config-4 output policy): for every element e of a
 // year's record block [12][5][GNC], sum and sum of squares over the members of the handle, in float64 and
 // in member order (deterministic).  Thread = element; consecutive threads read consecutive addresses of one
@@ -1086,6 +1157,56 @@ extern "C" int greb_b200_ensemble_moments(greb_b200_t h, double* sum, double* su
   const size_t E = (size_t)12 * 5 * GNC;
   CK(cudaMemcpy(sum, h->d_ens, E * sizeof(double), cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(sumsq, h->d_ens + E, E * sizeof(double), cudaMemcpyDeviceToHost));
+  return GREB_OK;
+}
+
+// ---- column physics of a step on tiles (include/greb_b200.h) ------------------------------------------
+extern "C" int greb_b200_tile_phase(int device, int arith, int phase, int ntiles, const greb_physics_par* p, float co2,
+                                    const float* forc, const float* sw_solar, const int* mask, const float* z_ocean,
+                                    const float* wz, float* corr, float* state, float* acc, float* stash,
+                                    const float* X) {
+  if (phase < 0 || phase > 2 || ntiles < 1 || !p || !forc || !sw_solar || !mask || !z_ocean || !wz || !corr || !state ||
+      !acc || !stash || (phase > 0 && !X) || (arith != GREB_ARITH_EXACT && arith != GREB_ARITH_FAST)) {
+    g_create_err = "greb_b200_tile_phase: bad arguments";
+    return GREB_E_INVALID;
+  }
+  if (cudaSetDevice(device) != cudaSuccess) {
+    g_create_err = "greb_b200_tile_phase: no such CUDA device; this library has no CPU fallback";
+    return GREB_E_NO_DEVICE;
+  }
+  GrebMemberConst mc;
+  greb_build_member_const(mc, *p, 0);   // the row tables are not used here
+  GrebMemberConst* d_mc = nullptr;
+  if (cudaMalloc((void**)&d_mc, sizeof mc) != cudaSuccess ||
+      cudaMemcpy(d_mc, &mc, sizeof mc, cudaMemcpyHostToDevice) != cudaSuccess) {
+    g_create_err = "greb_b200_tile_phase: CUDA allocation failed";
+    return GREB_E_CUDA;
+  }
+  GrebTileArgs ta;
+  ta.phase = phase;
+  ta.ntiles = ntiles;
+  ta.co2 = co2;
+  ta.mc = d_mc;
+  ta.forc = forc;
+  ta.sw_solar = sw_solar;
+  ta.mask = mask;
+  ta.z_ocean = z_ocean;
+  ta.wz = wz;
+  ta.corr = corr;
+  ta.state = state;
+  ta.acc = acc;
+  ta.stash = stash;
+  ta.X = X;
+  // the legacy default stream: ordered with the caller's own work on it (torch's default stream)
+  if (arith == GREB_ARITH_FAST) greb_tile_phase_kernel<1><<<ntiles, GREB_NMAIN * 32>>>(ta);
+  else greb_tile_phase_kernel<0><<<ntiles, GREB_NMAIN * 32>>>(ta);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  cudaFree(d_mc);
+  if (e != cudaSuccess) {
+    g_create_err = std::string("greb_b200_tile_phase: ") + cudaGetErrorString(e);
+    return GREB_E_CUDA;
+  }
   return GREB_OK;
 }
 

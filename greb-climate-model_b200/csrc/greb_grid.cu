@@ -516,6 +516,17 @@ extern "C" int greb_grid_set_fields(greb_grid_t h, const float* X, const float* 
   return 0;
 }
 
+// the winds of another step (full global host fields), levels and buffers untouched
+extern "C" int greb_grid_set_winds(greb_grid_t h, const float* u, const float* v) {
+  if (!h || !u || !v) return h ? gfail(h, "greb_grid_set_winds: null pointer") : -1;
+  if (!h->have_fields) return gfail(h, "greb_grid_set_winds: set_fields first");
+  cudaSetDevice(h->device);
+  const size_t off = (size_t)h->kbase * h->nx, fb = (size_t)h->nrows * h->nx * sizeof(float);
+  GCK(cudaMemcpy(h->d_u, u + off, fb, cudaMemcpyHostToDevice));
+  GCK(cudaMemcpy(h->d_v, v + off, fb, cudaMemcpyHostToDevice));
+  return 0;
+}
+
 extern "C" int greb_grid_substeps_async(greb_grid_t h, int n);
 extern "C" int greb_grid_sync(greb_grid_t h);
 

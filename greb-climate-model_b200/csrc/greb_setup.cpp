@@ -224,6 +224,10 @@ int greb_build_member_const(GrebMemberConst& mc, const greb_physics_par& p, int 
                           &mc.n_hslots, warp_order);
 }
 
+void greb_b200_wz(const float* z_topo, float h_scale, float* out, long n) {  // f:201-202 for any number of cells
+  for (long c = 0; c < n; ++c) out[c] = expf(-z_topo[c] / h_scale);
+}
+
 void greb_build_wz(float* out, const GrebHostForcing& F, const greb_physics_par& p) {
   for (int c = 0; c < GNC; ++c) {
     out[c] = expf(-F.z_topo[c] / p.z_air);          // f:201 (== exp(-z_topo/z_air) of f:420, 458)

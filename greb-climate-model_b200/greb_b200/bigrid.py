@@ -25,7 +25,7 @@ from . import sharding
 GRID_SYMBOLS = ["greb_grid_create", "greb_grid_destroy", "greb_grid_last_error", "greb_grid_set_geometry",
                 "greb_grid_set_fields", "greb_grid_substeps", "greb_grid_substeps_async", "greb_grid_sync", "greb_grid_view", "greb_grid_halo_refreshed",
                 "greb_grid_get", "greb_grid_last_ms", "greb_grid_ipc_bytes", "greb_grid_ipc_export", "greb_grid_ipc_import",
-                "greb_grid_run_persistent"]
+                "greb_grid_run_persistent", "greb_grid_set_winds"]
 _grid = None
 
 
@@ -48,6 +48,7 @@ def load_grid_library():
     L.greb_grid_last_error.restype = C.c_char_p
     L.greb_grid_set_geometry.argtypes = [vp, C.c_float, C.c_float, ip, fp]
     L.greb_grid_set_fields.argtypes = [vp, fp, fp, fp, fp]
+    L.greb_grid_set_winds.argtypes = [vp, fp, fp]
     L.greb_grid_substeps.argtypes = [vp, C.c_int]
     L.greb_grid_substeps_async.argtypes = [vp, C.c_int]
     L.greb_grid_sync.argtypes = [vp]
@@ -124,6 +125,12 @@ class DeviceBand:
         arrs = [np.ascontiguousarray(a, dtype=np.float32) for a in (X, wz, u, v)]
         assert all(a.shape == (self.ny, self.nx) for a in arrs)
         self._ck(self.L.greb_grid_set_fields(self.h, *[_lib._p(a) for a in arrs]), "greb_grid_set_fields")
+
+    def set_winds(self, u, v):
+        """the winds of another step (full global host fields); field, level and halos stay"""
+        arrs = [np.ascontiguousarray(a, dtype=np.float32) for a in (u, v)]
+        assert all(a.shape == (self.ny, self.nx) for a in arrs)
+        self._ck(self.L.greb_grid_set_winds(self.h, *[_lib._p(a) for a in arrs]), "greb_grid_set_winds")
 
     def substeps(self, n: int):
         self._ck(self.L.greb_grid_substeps(self.h, n), "greb_grid_substeps")
@@ -379,3 +386,167 @@ def bench_persistent(forcing, rank: int, world: int, device: int, substeps: int 
             "unit": "steps/s", "scaling": "strong", "n_gpus": world, "grid": f"{nx}x{ny}", "substeps_timed_per_field": substeps,
             "substeps_per_circulation": nsub, "us_per_substep": 1e3 * kms / substeps, "wall_steps_per_s": steps / wall,
             "path": "persistent cooperative kernel; halo rows pushed GPU to GPU inside the kernel (CUDA IPC + flags)"}
+
+
+# ------------------------------------------------------------------------------------------------
+#   A WHOLE 12-hour step on a grid of any size: column physics on tiles + the two circulations
+# ------------------------------------------------------------------------------------------------
+TILE = _lib.NC                       # 4,608 cells, laid out like an ensemble member
+GF_COUNT, GS_COUNT, GA_COUNT = 10, 5, 6
+
+
+class BigStep:
+    """One latitude band [k0, k1) of one member on a grid xdim x ydim (xdim a multiple of 96), stepped through
+    whole 12-hour steps (src/greb.f90:239-308): the cell-local physics runs on tiles of 4,608 consecutive cells
+    through greb_b200_tile_phase (the member kernel's own column functions), the two circulations through the
+    band's DeviceBands (persistent path; the only exchange between ranks).  `static` = dict of FULL global
+    host fields z_topo, glacier, mld_max (for z_ocean = 3 * max over the year, f:179-183); `step_forcing(it)`
+    returns the FULL global host fields of step `it`: tclim, swet, u, v, mld, mld_prev, cld and solar [ydim].
+    Flux corrections are zero unless set in `self.corr` ([ntiles][3][4608], device)."""
+
+    def __init__(self, nx, ny, static, state0, physics=None, rank=0, world=1, device=0, arith="exact", group=None):
+        import torch
+        if nx % _lib.XD:
+            raise ValueError("xdim must be a multiple of 96 (one solar value per 96-cell segment)")
+        self.t = torch
+        self.nx, self.ny, self.rank, self.world, self.device = nx, ny, rank, world, device
+        self.k0, self.k1 = band_range(ny, world, rank)
+        self.ncell = (self.k1 - self.k0) * nx
+        self.nt = -(-self.ncell // TILE)
+        self.p = physics if physics is not None else _lib.default_physics()
+        self.arith = {"exact": 0, "fast": 1}[arith]
+        self.L = _lib.load_library()
+        dev = f"cuda:{device}"
+        self.dev = dev
+        sl = slice(self.k0, self.k1)
+        f32 = np.float32
+        z = np.ascontiguousarray(static["z_topo"][sl], dtype=f32)
+        gl = np.ascontiguousarray(static["glacier"][sl], dtype=f32)
+        mask = ((z >= 0) * 1 + (z < 0) * 2 + (gl > 0.5) * 4 + (z > 0) * 8).astype(np.int32)
+        zoc = (f32(3.0) * np.ascontiguousarray(static["mld_max"][sl], dtype=f32)).astype(f32)
+        wz = np.stack([_lib.wz_field(z, self.p.z_air), _lib.wz_field(z, self.p.z_vapor)])   # glibc expf, like greb_setup
+        self.z_topo = z
+        self.zoc = zoc
+        self.mask = self._tiles(mask.astype(np.int32), dtype=torch.int32)
+        self.z_ocean = self._tiles(zoc)
+        self.wz = torch.stack([self._tiles(wz[0]), self._tiles(wz[1])], dim=1).contiguous()       # [nt][2][TILE]
+        self.state = torch.stack([self._tiles(np.ascontiguousarray(state0[n][sl], dtype=f32))
+                                  for n in ("Ts", "Ta", "To", "q", "cap_surf")], dim=1).contiguous()   # [nt][5][TILE]
+        self.acc = torch.zeros((self.nt, GA_COUNT, TILE), dtype=torch.float32, device=dev)
+        self.stash = torch.zeros((self.nt, 2, TILE), dtype=torch.float32, device=dev)
+        self.corr = torch.zeros((self.nt, 3, TILE), dtype=torch.float32, device=dev)
+        self.X = torch.zeros((self.nt, TILE), dtype=torch.float32, device=dev)
+        self.forc = torch.zeros((self.nt, GF_COUNT, TILE), dtype=torch.float32, device=dev)
+        self.solar = torch.zeros((self.nt, _lib.YD), dtype=torch.float32, device=dev)
+        seg_row = (np.arange(self.nt * TILE) // _lib.XD * _lib.XD // nx).reshape(self.nt, _lib.YD, -1)[:, :, 0]
+        self.seg_row = np.minimum(seg_row, self.k1 - self.k0 - 1)             # band row of every 96-cell segment
+        # the two circulating fields of the band (persistent path: 2 halo rows)
+        full = lambda a: np.ascontiguousarray(a, dtype=f32)
+        zfull = full(static["z_topo"])
+        wzf = [_lib.wz_field(zfull, self.p.z_air), _lib.wz_field(zfull, self.p.z_vapor)]
+        zero = np.zeros((ny, nx), dtype=f32)
+        self.bands = []
+        for i, name in enumerate(("Ta", "q")):
+            b = DeviceBand(nx, ny, self.k0, self.k1, 1, device=device, pi=self.p.pi, kappa=self.p.kappa)
+            b.set_fields(full(state0[name]), wzf[i], zero, zero)
+            self.bands.append(b)
+        self.grp = PersistentGroup(self.bands, rank, world, group)
+        self.nsub = self.bands[0].nsub
+        self.kernel_ms = 0.0
+
+    def close(self):
+        for b in getattr(self, "bands", []):
+            b.close()
+        self.bands = []
+
+    # natural (row-major) band field <-> tile layout: cell c = tile c // 4608, slot c % 4608; padded to whole tiles
+    def _tiles(self, a, dtype=None):
+        t = self.t
+        flat = np.ascontiguousarray(a).reshape(-1)
+        pad = self.nt * TILE - flat.size
+        if pad:
+            flat = np.concatenate([flat, np.repeat(flat[-1:], pad)])
+        x = t.from_numpy(flat.reshape(self.nt, TILE).copy()).to(self.dev)
+        return x if dtype is None else x.to(dtype)
+
+    def field(self, name) -> np.ndarray:
+        """the band's rows of a state field, host [k1-k0][xdim]"""
+        i = {"Ts": 0, "Ta": 1, "To": 2, "q": 3, "cap_surf": 4}[name]
+        return self.state[:, i, :].reshape(-1)[:self.ncell].cpu().numpy().reshape(self.k1 - self.k0, self.nx)
+
+    def _phase(self, phase, co2):
+        p = lambda x: C.c_void_p(x.data_ptr())
+        rc = self.L.greb_b200_tile_phase(self.device, self.arith, phase, self.nt, C.byref(self.p), C.c_float(co2),
+                                         p(self.forc), p(self.solar), p(self.mask), p(self.z_ocean), p(self.wz),
+                                         p(self.corr), p(self.state), p(self.acc), p(self.stash), p(self.X))
+        if rc != 0:
+            raise _lib.GrebError(f"greb_b200_tile_phase failed ({rc}): {self.L.greb_b200_last_error(None).decode()}")
+
+    def _circulate(self, band_index, state_index):
+        """X = the state field -> band buffer (own rows + the neighbours' 2 halo rows), nsub sub-steps, back"""
+        t = self.t
+        b = self.bands[band_index]
+        rows = self.k1 - self.k0
+        nat = self.state[:, state_index, :].reshape(-1)[:self.ncell].reshape(rows, self.nx)
+        b.rows(self.k0, self.k1).copy_(nat)
+        t.cuda.synchronize()
+        if self.world > 1:
+            exchange_halos(b, self.rank, self.world)          # the field's halo rows at the start of the circulation
+            import torch.distributed as dist
+            dist.barrier()
+        return b
+
+    def _load_forcing(self, f):
+        """the step's forcing -> tiles (host arithmetic = greb_setup.cpp's, fp32 IEEE), solar per segment, winds"""
+        t, f32 = self.t, np.float32
+        sl = slice(self.k0, self.k1)
+        u, v = (np.ascontiguousarray(f[n][sl], dtype=f32) for n in ("u", "v"))
+        mld, mldp = (np.ascontiguousarray(f[n][sl], dtype=f32) for n in ("mld", "mld_prev"))
+        aw = np.sqrt(u * u + v * v).astype(f32)                                        # f:452
+        aw = np.where(self.z_topo > 0, np.sqrt(aw * aw + f32(2.0) * f32(2.0)).astype(f32), aw)   # f:453
+        aw = np.where(self.z_topo < 0, np.sqrt(aw * aw + f32(3.0) * f32(3.0)).astype(f32), aw)   # f:454
+        dmld = (mld - mldp).astype(f32)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            rdeep = (dmld / (self.zoc - mld)).astype(f32)
+            rmix = (dmld / mld).astype(f32)
+        dtrad = (f32(-0.16) * np.ascontiguousarray(f["tclim"][sl], dtype=f32) - f32(5.0)).astype(f32)   # f:176
+        fields = [u, v, np.ascontiguousarray(f["cld"][sl], dtype=f32), dtrad, np.ascontiguousarray(f["swet"][sl], dtype=f32),
+                  aw, mld, dmld, rdeep, rmix]
+        self.forc.copy_(t.stack([self._tiles(a) for a in fields], dim=1))
+        sol = np.ascontiguousarray(f["solar"], dtype=f32)[self.k0:self.k1]
+        self.solar.copy_(t.from_numpy(sol[self.seg_row].astype(f32)).to(self.dev))
+        for b in self.bands:
+            b.set_winds(f["u"], f["v"])
+
+    def step(self, it, forcing_of_step, co2):
+        """one time_loop call (f:239-274) with step counter `it` (1-based; the caller's calendar picks the forcing)"""
+        self._load_forcing(forcing_of_step)
+        self._phase(0, co2)
+        # circulation(Ta) and circulation(q) (f:301, f:303) both start from the fields of the step's beginning and
+        # do not depend on each other: they run as ONE two-field persistent launch
+        for bi, si in ((0, 1), (1, 3)):
+            self._circulate(bi, si)
+        self.grp.advance(self.nsub)
+        self.kernel_ms += self.grp.kernel_ms
+        self.grp.kernel_ms = 0.0
+        for bi, ph in ((0, 1), (1, 2)):
+            self.X.reshape(-1)[:self.ncell].copy_(self.bands[bi].rows(self.k0, self.k1).reshape(-1))
+            self._phase(ph, co2)
+
+
+def s0_static_and_forcing(forcing, nx, ny):
+    """BigStep inputs from the synthetic S0 set (bilinearly upsampled when the grid is not 96x48): the static
+    dict and a function it -> the fields of step it"""
+    up = (lambda a: np.ascontiguousarray(a, dtype=np.float32)) if (nx, ny) == (_lib.XD, _lib.YD) else (lambda a: upsample(a, ny, nx))
+    static = {"z_topo": up(forcing.z_topo), "glacier": up(forcing.glacier), "mld_max": up(forcing.mldclim.max(axis=0))}
+    lat_src = (np.arange(_lib.YD) + 0.5) / _lib.YD
+    lat_dst = (np.arange(ny) + 0.5) / ny
+
+    def step_forcing(it):
+        n = (it - 1) % _lib.NT
+        npv = n - 1 if n > 0 else _lib.NT - 1
+        sol = forcing.sw_solar[n] if ny == _lib.YD else np.interp(lat_dst, lat_src, forcing.sw_solar[n]).astype(np.float32)
+        return {"tclim": up(forcing.tclim[n]), "swet": up(forcing.swetclim[n]), "u": up(forcing.uclim[n]),
+                "v": up(forcing.vclim[n]), "mld": up(forcing.mldclim[n]), "mld_prev": up(forcing.mldclim[npv]),
+                "cld": up(forcing.cldclim[n]), "solar": np.ascontiguousarray(sol, dtype=np.float32)}
+    return static, step_forcing

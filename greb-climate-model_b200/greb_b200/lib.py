@@ -32,7 +32,7 @@ ABI_SYMBOLS = ["greb_b200_physics_defaults", "greb_b200_physics_original", "greb
                "greb_b200_get_states_async", "greb_b200_sync_compute", "greb_b200_get_calendar",
                "greb_b200_set_calendar", "greb_b200_get_accumulators", "greb_b200_set_accumulators",
                "greb_b200_device_libm", "greb_b200_ensemble_moments", "greb_b200_ensemble_moments_device",
-               "greb_b200_fetch_monthly_async"]
+               "greb_b200_fetch_monthly_async", "greb_b200_tile_phase", "greb_b200_wz"]
 
 
 class Physics(C.Structure):
@@ -94,6 +94,8 @@ def load_library():
     L.greb_b200_set_switches.argtypes = [vp, C.c_int, C.c_uint]
     L.greb_b200_pad_co2.argtypes = [fp, C.c_int, fp, C.c_int]
     L.greb_b200_pad_co2.restype = None
+    L.greb_b200_wz.argtypes = [fp, C.c_float, fp, C.c_long]
+    L.greb_b200_wz.restype = None
     L.greb_b200_init.argtypes = [vp]
     L.greb_b200_spinup.argtypes = [vp, C.c_int]
     L.greb_b200_reset_scenario.argtypes = [vp]
@@ -122,6 +124,7 @@ def load_library():
     L.greb_b200_circulation.argtypes = [vp, C.c_int, C.c_int, fp, fp, fp, C.c_int]
     L.greb_b200_last_kernel_ms.argtypes = [vp, fp, ip]
     L.greb_b200_device_libm.argtypes = [vp, C.c_int, fp, fp, C.c_int]
+    L.greb_b200_tile_phase.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Physics), C.c_float] + [vp] * 10
     L.greb_b200_ensemble_moments.argtypes = [vp, vp, vp]
     L.greb_b200_ensemble_moments_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), ip]
     _lib = L
@@ -138,6 +141,14 @@ def original_physics() -> Physics:
     p = Physics()
     load_library().greb_b200_physics_original(C.byref(p))
     return p
+
+
+def wz_field(z_topo, h_scale: float) -> np.ndarray:
+    """exp(-z_topo / h_scale) with the library's host libm (reference src/greb.f90:201-202), any shape"""
+    z = np.ascontiguousarray(z_topo, dtype=np.float32)
+    out = np.empty_like(z)
+    load_library().greb_b200_wz(_p(z), h_scale, _p(out), z.size)
+    return out
 
 
 def pad_co2(given, n_years: int) -> np.ndarray:

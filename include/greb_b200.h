@@ -126,6 +126,9 @@ enum {
   GREB_SW_ALL = 255
 };
 int greb_b200_set_switches(greb_b200_t h, int member, unsigned mask);
+/* wz = exp(-z_topo / h_scale) (src/greb.f90:201-202: wz_air with z_air, wz_vapor with z_vapor) for n cells,
+ * evaluated on the host with the libm the rest of the set-up uses (hosts of grids other than 96x48). */
+void greb_b200_wz(const float* z_topo, float h_scale, float* out, long n);
 /* src/greb.f90:1047-1061: `n_given` values followed by padding to n_years (first<0 -> 680). */
 void greb_b200_pad_co2(const float* given, int n_given, float* co2_ppm, int n_years);
 
@@ -231,6 +234,21 @@ int greb_b200_circulation(greb_b200_t h, int member, int ityr, const float* X_in
  * log (src/greb.f90:422-424, 457) with glibc's libm; the exact mode restates glibc's algorithm on the
  * device so that whole runs, not only the circulation, are bit-identical (greb_simt.h). */
 int greb_b200_device_libm(greb_b200_t h, int which, const float* x, float* y, int n);
+
+/* Column physics of one 12-h step on TILES — the cell-local part of `tendencies` + the `time_loop` updates
+ * (src/greb.f90:277-308, 258-272: SWradiation, LWradiation, sensible heat, hydro, deep_ocean, seaice) for a
+ * grid of any size (BASELINE.json configs[4]); the circulations come from include/greb_grid.h.  A band of the
+ * grid is cut into tiles of 4,608 consecutive cells laid out like an ensemble member; all pointers are
+ * DEVICE pointers: forc [ntiles][10][4608] (u, v, cld, dTrad, swet, abswind, mld, dmld, dmld/(z_ocean-mld),
+ * dmld/mld of the step), sw_solar [ntiles][48] (one value per 96-cell segment), mask [ntiles][4608] (bit 0:
+ * z_topo >= 0, 1: < 0, 2: glacier, 3: > 0), z_ocean, wz [ntiles][2][4608] (air, vapour), corr [ntiles][3][4608]
+ * (TF, ToF, qF of the step), state [ntiles][5][4608], acc [ntiles][6][4608], stash [ntiles][2][4608] (carries
+ * the tendencies from phase 0 to phases 1, 2), X [ntiles][4608] = the circulated field.  phase 0 = before the
+ * circulations, 1 = after circulation(Ta), 2 = after circulation(q).  Runs on the legacy default stream and
+ * returns when done.  The same device code as the member kernel: at 96x48 a step is bit-identical to it. */
+int greb_b200_tile_phase(int device, int arith, int phase, int ntiles, const greb_physics_par* p, float co2,
+                         const float* forc, const float* sw_solar, const int* mask, const float* z_ocean,
+                         const float* wz, float* corr, float* state, float* acc, float* stash, const float* X);
 
 /* ---- timing of the last spinup/run call (CUDA events on the launch stream, ms) -------------- */
 int greb_b200_last_kernel_ms(greb_b200_t h, float* ms, int* launches);

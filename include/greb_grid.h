@@ -34,6 +34,10 @@ int greb_grid_set_geometry(greb_grid_t h, float pi, float kappa, int* nsub, floa
  * X = the circulating field (Ta or q), wz = wz_air or wz_vapor, u/v = the wind climatology of the step */
 int greb_grid_set_fields(greb_grid_t h, const float* X, const float* wz, const float* u, const float* v);
 
+/* the wind climatology of another step (FULL global host fields); the circulating field, its level and the
+ * halo bookkeeping are untouched — how a host steps through the calendar (src/greb.f90:251-252) */
+int greb_grid_set_winds(greb_grid_t h, const float* u, const float* v);
+
 /* n more sub-steps X = (X + dx_diffuse) + dx_advec (f:546-549) without communication; fails if the
  * halo is too thin for n (exchange first). */
 int greb_grid_substeps(greb_grid_t h, int n);

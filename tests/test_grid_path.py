@@ -313,3 +313,64 @@ def test_neighbour_handle_exchange_gloo_world3():
             if r < world - 1:
                 want[1] = f"blob-rank{r + 1}-field{f}"
             assert ret[r][f] == want, (r, f, ret[r][f])
+
+
+@pytest.mark.gpu
+def test_whole_step_on_tiles_equals_the_member_kernel_at_96x48(forcing):
+    """BigStep = column physics on tiles (the member kernel's own device functions) + the big-grid circulations:
+    on the reference grid six 12-hour steps are bit-identical to the ensemble kernel (exact mode)"""
+    import greb_b200
+    ens = greb_b200.Ensemble(1)
+    ens.set_forcing(forcing)
+    ens.set_member(0, greb_b200.default_physics(), [680.0])
+    ens.init()
+    names = ("Ts", "Ta", "To", "q", "cap_surf")
+    state0 = {n: ens.get_state(0, n) for n in names}
+    static, step_forcing = bigrid.s0_static_and_forcing(forcing, 96, 48)
+    big = bigrid.BigStep(96, 48, static, state0)
+    assert big.nt == 1 and big.nsub == 24
+    for it in range(1, 7):
+        ens.time_loop(it)
+        big.step(it, step_forcing(it), 680.0)
+        for n in names:
+            a, b = ens.get_state(0, n), big.field(n)
+            assert np.array_equal(np.where(a == 0, np.float32(0), a), np.where(b == 0, np.float32(0), b)), \
+                (it, n, float(np.abs(a - b).max()))
+    big.close()
+    ens.close()
+
+
+@pytest.mark.gpu
+def test_column_physics_on_a_big_grid_is_cell_local(forcing):
+    """1440x720 built from 15x15 copies of the 96x48 inputs: phase A (SW, LW, sensible, hydro, deep ocean, Ts/To/
+    cap update, sea ice) of every copy equals the 96x48 result bit for bit — tiles of 4,608 cells, segments
+    of 96, padding and the per-segment solar values are all in the right place"""
+    import greb_b200
+    names = ("Ts", "Ta", "To", "q", "cap_surf")
+    static, step_forcing = bigrid.s0_static_and_forcing(forcing, 96, 48)
+    rng = np.random.default_rng(4)
+    state0 = {"Ts": forcing.tclim[729] + rng.uniform(-3, 3, (48, 96)).astype(np.float32), "Ta": forcing.tclim[729].copy(),
+              "To": forcing.tclim[729] - np.float32(1.0), "q": forcing.qclim[729].copy(),
+              "cap_surf": np.where(forcing.z_topo > 0, np.float32(4.8e6), np.float32(2.1e8)).astype(np.float32)}
+    f1 = step_forcing(100)
+    small = bigrid.BigStep(96, 48, static, state0)
+    small.step(100, f1, 560.0)
+    tile = lambda a: np.tile(a, (15, 15))
+    staticB = {k: tile(v) for k, v in static.items()}
+    stateB = {k: tile(v) for k, v in state0.items()}
+    # np.tile repeats the 48 rows 15 times: row r of the big grid = row r % 48 of the small one
+    fB = {k: (np.tile(v, 15) if k == "solar" else tile(v)) for k, v in f1.items()}
+    big = bigrid.BigStep(1440, 720, staticB, stateB)
+    assert big.nt == 225
+    # phase A only (whole steps at 1440x720 are timed by tools/run_bigrid.py): forcing as step() loads it
+    big._load_forcing(fB)
+    big._phase(0, 560.0)
+    small2 = bigrid.BigStep(96, 48, static, state0)
+    small2._load_forcing(f1)
+    small2._phase(0, 560.0)
+    for n in ("Ts", "To", "cap_surf"):
+        assert np.array_equal(big.field(n), tile(small2.field(n))), n
+    assert np.array_equal(big.stash[:, 0].reshape(-1).cpu().numpy().reshape(720, 1440),
+                          tile(small2.stash[:, 0].reshape(48, 96).cpu().numpy()))
+    for b in (small, small2, big):
+        b.close()

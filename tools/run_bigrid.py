@@ -28,6 +28,78 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "greb-climate-model_b200"))
 
 
+def whole_steps(args, f, rank, world, local):
+    """BASELINE.json configs[4] with the column physics: N whole 12-hour steps of one member on nx x ny"""
+    import torch
+    import torch.distributed as dist
+    import greb_b200
+    from greb_b200 import bigrid
+    nx, ny, n = args.nx, args.ny, args.whole_steps
+    static, step_forcing = bigrid.s0_static_and_forcing(f, nx, ny)
+    p = greb_b200.default_physics()
+    f32 = np.float32
+    up = (lambda a: np.ascontiguousarray(a, dtype=f32)) if (nx, ny) == (96, 48) else (lambda a: bigrid.upsample(a, ny, nx))
+    toclim = np.minimum.reduce(f.tclim, axis=0)
+    toclim = np.where(toclim - f32(273.15) < f32(-1.7), f32(-1.7) + f32(273.15), toclim).astype(f32)     # f:1087-1094
+    cap_land = f32(f32(p.cp_land) * f32(p.rho_land)) * f32(p.d_land)
+    cap_ocean = f32(p.cp_ocean) * f32(p.rho_ocean)
+    z = static["z_topo"]
+    state0 = {"Ts": up(f.tclim[729]), "Ta": up(f.tclim[729]), "To": up(toclim), "q": up(f.qclim[729]),
+              "cap_surf": np.where(z > 0, cap_land, cap_ocean * up(f.mldclim[0])).astype(f32)}     # f:190-197
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def run(rk, wd, steps, timed_from):
+        big = bigrid.BigStep(nx, ny, static, state0, rank=rk, world=wd, device=local)
+        barrier() if wd > 1 else torch.cuda.synchronize()
+        t0 = None
+        for it in range(1, steps + 1):
+            if it == timed_from:
+                barrier() if wd > 1 else torch.cuda.synchronize()
+                t0 = time.perf_counter()
+            big.step(it, step_forcing(it), 680.0)
+        barrier() if wd > 1 else torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        out = {nme: big.field(nme) for nme in ("Ts", "Ta", "To", "q")}
+        kms = big.kernel_ms
+        if wd > 1:
+            dist.barrier()
+        big.close()
+        return out, wall, kms
+
+    mine, wall, kms = run(rank, world, 1 + n, 2)                 # step 1 is the warm-up
+    checks = {}
+    if world > 1:
+        sizes = [bigrid.band_range(ny, world, r) for r in range(world)]
+        pad = max(hi - lo for lo, hi in sizes)
+        full = {}
+        for nme, a in mine.items():
+            buf = torch.zeros((pad, nx), dtype=torch.float32, device=f"cuda:{local}")
+            buf[:a.shape[0]] = torch.from_numpy(a).to(f"cuda:{local}")
+            allb = [torch.empty_like(buf) for _ in range(world)]
+            dist.all_gather(allb, buf)
+            full[nme] = torch.cat([allb[r][:hi - lo] for r, (lo, hi) in enumerate(sizes)]).cpu().numpy()
+        if rank == 0:
+            one, _, _ = run(0, 1, 1 + n, 2)
+            checks[f"{world}_gpu_equals_1_gpu_after_{1 + n}_whole_steps"] = bool(all(np.array_equal(one[k], full[k]) for k in one))
+        dist.barrier()
+    t = torch.tensor([wall], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        line = {"metric": "whole 12-hour steps/s (column physics + both circulations of one member)", "value": n / float(t[0]),
+                "unit": "steps/s", "n_gpus": world, "scaling": "strong", "grid": f"{nx}x{ny}", "steps_timed": n,
+                "path": "column physics on tiles of 4,608 cells (greb_b200_tile_phase, the member kernel's device functions) + "
+                        "persistent dataflow circulations; per step the host uploads the step's forcing and exchanges the "
+                        "fields' 2 halo rows once per circulation",
+                "circulation_kernel_s_per_step_rank0": kms / 1e3 / (1 + n), "mean_Ts_K": float(mine["Ts"].mean()),
+                "finite": bool(all(np.isfinite(a).all() for a in mine.values())), "checks": checks}
+        print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--nx", type=int, default=1440)
@@ -40,6 +112,9 @@ def main():
                     help="v2 path: one cooperative launch per call, both fields in it, halo rows pushed GPU to GPU by "
                          "the kernel (CUDA IPC peer memory + flags); the host is not in the loop (--period is ignored)")
     ap.add_argument("--chunk", type=int, default=1350, help="--persistent: sub-steps per cooperative launch")
+    ap.add_argument("--whole-steps", type=int, default=0,
+                    help="time N WHOLE 12-hour steps instead: column physics on tiles (greb_b200_tile_phase) + the two "
+                         "circulations on the persistent path; checks N GPUs == 1 GPU bit for bit first")
     args = ap.parse_args()
 
     import torch
@@ -61,6 +136,12 @@ def main():
 
     nx, ny, s = args.nx, args.ny, (1 if args.persistent else args.s)
     f = synth.cached_forcing(cache_dir=os.environ.get("GREB_FORCING_CACHE", "/tmp/greb_b200_cache"))
+    if args.whole_steps > 0:
+        whole_steps(args, f, rank, world, local)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
     ityr = 200
     topo = upsample(f.z_topo, ny, nx)
     fld = {"Ta": (upsample(f.tclim[ityr - 1], ny, nx), np.exp(-topo / np.float32(8400.0)).astype(np.float32)),

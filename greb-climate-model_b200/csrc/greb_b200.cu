@@ -16,6 +16,7 @@
 
 #include "../../include/greb_b200.h"
 #include "greb_core.h"
+#include "greb_core6.h"
 #include "greb_setup.h"
 
 // ------------------------------------------------------------------------------------------------
@@ -205,6 +206,34 @@ __global__ void __launch_bounds__(256) greb_ensemble_moments_kernel(const float*
   }
   sum[e] = s;
   sq[e] = q;
+}
+
+// circulation on 6-cell tiles (greb_core6.h): 24 warps, no helper warps; exact mode
+#define T6_SMEM_BYTES (T6_FLOATS * (int)sizeof(float))
+__global__ void __launch_bounds__(T6_NTHREADS, 1) greb_circulation6_kernel(const GrebCirculationArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  __shared__ GrebMemberConst mc_s;
+  {
+    const int* s = reinterpret_cast<const int*>(a.mc);
+    int* d = reinterpret_cast<int*>(&mc_s);
+    for (int i = threadIdx.x; i < (int)(sizeof(GrebMemberConst) / sizeof(int)); i += blockDim.x) d[i] = s[i];
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const Row6 g = row6(warp, lane, mc_s);
+  Tile6 t;
+  const size_t off = (size_t)blockIdx.x * GNC;
+  t6_load_uv(t, g, a.uv, a.uv + GNC, smem);
+  t6_load_wz(t, g, a.wz + off, smem);
+  t6_load_field(t, g, a.X_in + off);
+  int phase = 0;
+  t6_circulation(t, g, mc_s, smem + T6_HB, smem, phase, ((a.late_mask >> warp) & 1u) != 0);
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    const int idx = g.k * GX + g.col + 2 * q;
+    const float2 x = *reinterpret_cast<const float2*>(a.X_in + off + idx);
+    *reinterpret_cast<float2*>(a.dX + off + idx) = make_float2(t.T[2 * q] - x.x, t.T[2 * q + 1] - x.y);   // f:551
+  }
 }
 
 // expf / logf of the exact mode on n arguments (parity entry greb_b200_device_libm)
@@ -1037,8 +1066,17 @@ extern "C" int greb_b200_circulation(greb_b200_t h, int member, int ityr, const 
   a.dX = dO;
   a.warp_map = pack_map(h->layout.map);
   a.late_mask = h->layout.late;
+  const char* t6 = getenv("GREB_B200_TILE6");
+  if (t6 && h->arith == GREB_ARITH_EXACT) {   // experiment: 6-cell tiles, 24 warps (greb_core6.h)
+    unsigned late = 0x0f0f0fu;                // every other warp of a sub-partition does its x part after the barrier
+    if (t6[0] == '0') late = 0;
+    sscanf(t6, "%x", &late);
+    a.late_mask = late & 0xffffffu;
+    cudaFuncSetAttribute(greb_circulation6_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T6_SMEM_BYTES);
+  }
   CK(cudaEventRecord(h->ev0, h->stream));
-  if (h->arith == GREB_ARITH_FAST) greb_circulation_kernel<1><<<n, GREB_NTHREADS, GREB_SMEM_BYTES, h->stream>>>(a);
+  if (t6 && h->arith == GREB_ARITH_EXACT) greb_circulation6_kernel<<<n, T6_NTHREADS, T6_SMEM_BYTES, h->stream>>>(a);
+  else if (h->arith == GREB_ARITH_FAST) greb_circulation_kernel<1><<<n, GREB_NTHREADS, GREB_SMEM_BYTES, h->stream>>>(a);
   else greb_circulation_kernel<0><<<n, GREB_NTHREADS, GREB_SMEM_BYTES, h->stream>>>(a);
   CK(cudaEventRecord(h->ev1, h->stream));
   CK(cudaGetLastError());

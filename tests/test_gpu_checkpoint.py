@@ -164,3 +164,40 @@ def test_ensemble_field_moments_on_the_device(forcing):
     mean, var, cnt = sharding.reduce_field_moments(e, e.n)         # single rank: no collective
     assert cnt == 5 and np.allclose(mean, o.mean(0), rtol=1e-14) and np.allclose(var, o.var(0), rtol=1e-6, atol=1e-9)
     e.close()
+
+
+def test_async_state_upload_and_device_views(forcing):
+    """greb_b200_set_states_async (pinned upload behind the compute stream), greb_b200_diag_device and
+    greb_b200_ensemble_moments_device (the vectors a multi-GPU driver reduces) against their host-side twins"""
+    import torch
+    ps, co2 = _members()
+    a = make_ensemble(forcing, ps, co2)
+    a.spinup(1)
+    a.reset_scenario()
+    _, gm1, gmc1 = a.run(1)
+    st1 = a.get_states()
+    out2, gm2, gmc2 = a.run(1)
+    # rewind: upload the year-1 states through the asynchronous entry, set the calendar, run year 2 again
+    pin = torch.from_numpy(st1.copy()).pin_memory()
+    a.set_states_async(pin.data_ptr())
+    a.wait()
+    assert np.array_equal(a.get_states(), st1)
+    a.set_calendar(730 + 1)
+    out2b, gm2b, gmc2b = a.run(1)
+    assert np.array_equal(out2b, out2) and np.array_equal(gm2b, gm2) and np.array_equal(gmc2b, gmc2)
+
+    class _View:
+        def __init__(self, ptr, n, typestr):
+            self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, True), "version": 2}
+
+    ptr, n = a.diag_device()
+    assert n == 2 * a.n
+    d = torch.as_tensor(_View(ptr, n, "<f4"), device="cuda:0").cpu().numpy().reshape(a.n, 2)
+    assert np.array_equal(d[:, 0], gm2b[:, -1]) and np.array_equal(d[:, 1], gmc2b[:, -1])
+    s, q = a.ensemble_moments()
+    pS, pQ, ne = a.ensemble_moments_device()
+    assert ne == 12 * 5 * 48 * 96
+    assert np.array_equal(torch.as_tensor(_View(pS, ne, "<f8"), device="cuda:0").cpu().numpy(), s.ravel())
+    assert np.array_equal(torch.as_tensor(_View(pQ, ne, "<f8"), device="cuda:0").cpu().numpy(), q.ravel())
+    assert not a.flags().any()
+    a.close()

@@ -64,10 +64,12 @@ def load_grid_library():
     return L
 
 
-def upsample(a: np.ndarray, ny: int, nx: int) -> np.ndarray:
-    """bilinear upsample of a [48][96] cell-centred field (periodic in longitude, clamped at the poles)"""
+def upsample(a: np.ndarray, ny: int, nx: int, rows=None) -> np.ndarray:
+    """bilinear upsample of a [48][96] cell-centred field (periodic in longitude, clamped at the poles);
+    rows = (lo, hi): only those rows of the [ny][nx] result are computed (the same bits), the others are 0"""
     sy, sx = a.shape
-    y = (np.arange(ny) + 0.5) * sy / ny - 0.5
+    lo, hi = (0, ny) if rows is None else (max(int(rows[0]), 0), min(int(rows[1]), ny))
+    y = (np.arange(lo, hi) + 0.5) * sy / ny - 0.5
     x = (np.arange(nx) + 0.5) * sx / nx - 0.5
     y0 = np.clip(np.floor(y).astype(int), 0, sy - 1)
     y1 = np.clip(y0 + 1, 0, sy - 1)
@@ -78,7 +80,12 @@ def upsample(a: np.ndarray, ny: int, nx: int) -> np.ndarray:
     fx = (x - np.floor(x)).astype(np.float32)
     top = a[y0][:, x0] * (1 - fx) + a[y0][:, x1] * fx
     bot = a[y1][:, x0] * (1 - fx) + a[y1][:, x1] * fx
-    return np.ascontiguousarray(top * (1 - fy[:, None]) + bot * fy[:, None], dtype=np.float32)
+    block = np.ascontiguousarray(top * (1 - fy[:, None]) + bot * fy[:, None], dtype=np.float32)
+    if rows is None:
+        return block
+    out = np.zeros((ny, nx), dtype=np.float32)
+    out[lo:hi] = block
+    return out
 
 
 def band_range(ny: int, world: int, rank: int) -> Tuple[int, int]:
@@ -496,8 +503,11 @@ class BigStep:
             dist.barrier()
         return b
 
-    def _load_forcing(self, f):
-        """the step's forcing -> tiles (host arithmetic = greb_setup.cpp's, fp32 IEEE), solar per segment, winds"""
+    def stage_forcing(self, f):
+        """One step's forcing -> a staged set on the device: tiles (host arithmetic = greb_setup.cpp's, fp32 IEEE),
+        solar per segment, and the winds' host fields for the bands.  Touches nothing the running step uses (own
+        CUDA stream, pinned staging buffer, two device sets used in turn), so a worker thread may stage step
+        it+1 while step it runs (`run`)."""
         t, f32 = self.t, np.float32
         sl = slice(self.k0, self.k1)
         u, v = (np.ascontiguousarray(f[n][sl], dtype=f32) for n in ("u", "v"))
@@ -512,14 +522,47 @@ class BigStep:
         dtrad = (f32(-0.16) * np.ascontiguousarray(f["tclim"][sl], dtype=f32) - f32(5.0)).astype(f32)   # f:176
         fields = [u, v, np.ascontiguousarray(f["cld"][sl], dtype=f32), dtrad, np.ascontiguousarray(f["swet"][sl], dtype=f32),
                   aw, mld, dmld, rdeep, rmix]
-        self.forc.copy_(t.stack([self._tiles(a) for a in fields], dim=1))
+        if not hasattr(self, "_stage"):
+            with t.cuda.device(self.device):
+                self._stage_stream = t.cuda.Stream()
+            self._stage = [{"forc": t.empty_like(self.forc), "solar": t.empty_like(self.solar),
+                            "h_forc": t.empty(self.forc.shape, dtype=t.float32).pin_memory(),
+                            "h_solar": t.empty(self.solar.shape, dtype=t.float32).pin_memory(),
+                            "event": t.cuda.Event()} for _ in range(2)]
+            self._stage_seq = 0
+        st = self._stage[self._stage_seq % 2]
+        self._stage_seq += 1
+        st["event"].synchronize()                 # the previous upload into this set (its step is long over)
+        hf = st["h_forc"].numpy()
+        for j, a in enumerate(fields):            # natural band order -> tiles, the tail padded with the last cell
+            dst = hf[:, j, :]
+            src = a.reshape(-1)
+            full = src.size // TILE
+            dst[:full] = src[:full * TILE].reshape(full, TILE)
+            if full < self.nt:
+                rest = src.size - full * TILE
+                dst[full, :rest] = src[full * TILE:]
+                dst[full, rest:] = src[-1]
         sol = np.ascontiguousarray(f["solar"], dtype=f32)[self.k0:self.k1]
-        self.solar.copy_(t.from_numpy(sol[self.seg_row].astype(f32)).to(self.dev))
+        st["h_solar"].numpy()[...] = sol[self.seg_row]
+        with t.cuda.device(self.device), t.cuda.stream(self._stage_stream):
+            st["forc"].copy_(st["h_forc"], non_blocking=True)
+            st["solar"].copy_(st["h_solar"], non_blocking=True)
+            st["event"].record()
+        return {"_staged": st, "u": f["u"], "v": f["v"]}
+
+    def _load_forcing(self, f):
+        """make a step's forcing (host fields or a staged set) the current one"""
+        sf = f if "_staged" in f else self.stage_forcing(f)
+        st = sf["_staged"]
+        st["event"].synchronize()
+        self.forc, self.solar = st["forc"], st["solar"]
         for b in self.bands:
-            b.set_winds(f["u"], f["v"])
+            b.set_winds(sf["u"], sf["v"])
 
     def step(self, it, forcing_of_step, co2):
-        """one time_loop call (f:239-274) with step counter `it` (1-based; the caller's calendar picks the forcing)"""
+        """one time_loop call (f:239-274) with step counter `it` (1-based; the caller's calendar picks the forcing);
+        `forcing_of_step` = the FULL global host fields of the step, or what stage_forcing returned for them"""
         self._load_forcing(forcing_of_step)
         self._phase(0, co2)
         # circulation(Ta) and circulation(q) (f:301, f:303) both start from the fields of the step's beginning and
@@ -533,11 +576,33 @@ class BigStep:
             self.X.reshape(-1)[:self.ncell].copy_(self.bands[bi].rows(self.k0, self.k1).reshape(-1))
             self._phase(ph, co2)
 
+    def run(self, it0, nsteps, step_forcing, co2=680.0, prefetch=True):
+        """steps it0 .. it0+nsteps-1; with `prefetch` a worker thread prepares and uploads the forcing of step
+        it+1 (step_forcing(it+1) and stage_forcing) while step it runs on the device — the host arithmetic
+        and the H2D copy leave the critical path, the results are the same bits"""
+        co2_of = co2 if callable(co2) else (lambda it: co2)
+        if not prefetch or nsteps < 2:
+            for it in range(it0, it0 + nsteps):
+                self.step(it, step_forcing(it), co2_of(it))
+            return
+        from concurrent.futures import ThreadPoolExecutor
+        job = lambda it: self.stage_forcing(step_forcing(it))
+        with ThreadPoolExecutor(1) as pool:
+            nxt = pool.submit(job, it0)
+            for it in range(it0, it0 + nsteps):
+                staged = nxt.result()
+                if it + 1 < it0 + nsteps:
+                    nxt = pool.submit(job, it + 1)
+                self.step(it, staged, co2_of(it))
 
-def s0_static_and_forcing(forcing, nx, ny):
+
+def s0_static_and_forcing(forcing, nx, ny, rows=None):
     """BigStep inputs from the synthetic S0 set (bilinearly upsampled when the grid is not 96x48): the static
-    dict and a function it -> the fields of step it"""
-    up = (lambda a: np.ascontiguousarray(a, dtype=np.float32)) if (nx, ny) == (_lib.XD, _lib.YD) else (lambda a: upsample(a, ny, nx))
+    dict and a function it -> the fields of step it.  rows = (lo, hi): the step fields are filled in only for
+    those rows (a rank's band plus the 2 halo rows the winds need) — 1/N of the host work on N ranks."""
+    same = (nx, ny) == (_lib.XD, _lib.YD)
+    up = (lambda a: np.ascontiguousarray(a, dtype=np.float32)) if same else (lambda a: upsample(a, ny, nx))
+    ups = up if (same or rows is None) else (lambda a: upsample(a, ny, nx, rows))
     static = {"z_topo": up(forcing.z_topo), "glacier": up(forcing.glacier), "mld_max": up(forcing.mldclim.max(axis=0))}
     lat_src = (np.arange(_lib.YD) + 0.5) / _lib.YD
     lat_dst = (np.arange(ny) + 0.5) / ny
@@ -546,7 +611,7 @@ def s0_static_and_forcing(forcing, nx, ny):
         n = (it - 1) % _lib.NT
         npv = n - 1 if n > 0 else _lib.NT - 1
         sol = forcing.sw_solar[n] if ny == _lib.YD else np.interp(lat_dst, lat_src, forcing.sw_solar[n]).astype(np.float32)
-        return {"tclim": up(forcing.tclim[n]), "swet": up(forcing.swetclim[n]), "u": up(forcing.uclim[n]),
-                "v": up(forcing.vclim[n]), "mld": up(forcing.mldclim[n]), "mld_prev": up(forcing.mldclim[npv]),
-                "cld": up(forcing.cldclim[n]), "solar": np.ascontiguousarray(sol, dtype=np.float32)}
+        return {"tclim": ups(forcing.tclim[n]), "swet": ups(forcing.swetclim[n]), "u": ups(forcing.uclim[n]),
+                "v": ups(forcing.vclim[n]), "mld": ups(forcing.mldclim[n]), "mld_prev": ups(forcing.mldclim[npv]),
+                "cld": ups(forcing.cldclim[n]), "solar": np.ascontiguousarray(sol, dtype=np.float32)}
     return static, step_forcing

@@ -188,7 +188,7 @@ def test_async_state_upload_and_device_views(forcing):
 
     class _View:
         def __init__(self, ptr, n, typestr):
-            self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, True), "version": 2}
+            self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
 
     ptr, n = a.diag_device()
     assert n == 2 * a.n

@@ -336,6 +336,12 @@ def test_whole_step_on_tiles_equals_the_member_kernel_at_96x48(forcing):
             a, b = ens.get_state(0, n), big.field(n)
             assert np.array_equal(np.where(a == 0, np.float32(0), a), np.where(b == 0, np.float32(0), b)), \
                 (it, n, float(np.abs(a - b).max()))
+    # the same six steps with the forcing of step it+1 staged by a worker thread while step it runs
+    pre = bigrid.BigStep(96, 48, static, state0)
+    pre.run(1, 6, step_forcing, 680.0, prefetch=True)
+    for n in names:
+        assert np.array_equal(pre.field(n), big.field(n)), n
+    pre.close()
     big.close()
     ens.close()
 

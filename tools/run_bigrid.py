@@ -35,7 +35,7 @@ def whole_steps(args, f, rank, world, local):
     import greb_b200
     from greb_b200 import bigrid
     nx, ny, n = args.nx, args.ny, args.whole_steps
-    static, step_forcing = bigrid.s0_static_and_forcing(f, nx, ny)
+    static, step_forcing_full = bigrid.s0_static_and_forcing(f, nx, ny)
     p = greb_b200.default_physics()
     f32 = np.float32
     up = (lambda a: np.ascontiguousarray(a, dtype=f32)) if (nx, ny) == (96, 48) else (lambda a: bigrid.upsample(a, ny, nx))
@@ -53,14 +53,17 @@ def whole_steps(args, f, rank, world, local):
             dist.barrier()
 
     def run(rk, wd, steps, timed_from):
+        step_forcing = step_forcing_full
+        if wd > 1 and (nx, ny) != (96, 48):          # a rank prepares only its band (+ the winds' 2 halo rows)
+            lo, hi = bigrid.band_range(ny, wd, rk)
+            _, step_forcing = bigrid.s0_static_and_forcing(f, nx, ny, rows=(lo - 2, hi + 2))
         big = bigrid.BigStep(nx, ny, static, state0, rank=rk, world=wd, device=local)
         barrier() if wd > 1 else torch.cuda.synchronize()
-        t0 = None
-        for it in range(1, steps + 1):
-            if it == timed_from:
-                barrier() if wd > 1 else torch.cuda.synchronize()
-                t0 = time.perf_counter()
-            big.step(it, step_forcing(it), 680.0)
+        big.run(1, timed_from - 1, step_forcing, 680.0, prefetch=False)      # warm-up
+        barrier() if wd > 1 else torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        # the forcing of step it+1 is prepared and uploaded by a worker thread while step it runs (BigStep.run)
+        big.run(timed_from, steps - timed_from + 1, step_forcing, 680.0, prefetch=not args.no_prefetch)
         barrier() if wd > 1 else torch.cuda.synchronize()
         wall = time.perf_counter() - t0
         out = {nme: big.field(nme) for nme in ("Ts", "Ta", "To", "q")}
@@ -93,8 +96,9 @@ def whole_steps(args, f, rank, world, local):
         line = {"metric": "whole 12-hour steps/s (column physics + both circulations of one member)", "value": n / float(t[0]),
                 "unit": "steps/s", "n_gpus": world, "scaling": "strong", "grid": f"{nx}x{ny}", "steps_timed": n,
                 "path": "column physics on tiles of 4,608 cells (greb_b200_tile_phase, the member kernel's device functions) + "
-                        "persistent dataflow circulations; per step the host uploads the step's forcing and exchanges the "
-                        "fields' 2 halo rows once per circulation",
+                        "persistent dataflow circulations; per step the host prepares and uploads the step's forcing ("
+                        + ("in a worker thread, one step ahead" if not args.no_prefetch else "on the critical path") +
+                        ") and exchanges the fields' 2 halo rows once per circulation",
                 "circulation_kernel_s_per_step_rank0": kms / 1e3 / (1 + n), "mean_Ts_K": float(mine["Ts"].mean()),
                 "finite": bool(all(np.isfinite(a).all() for a in mine.values())), "checks": checks}
         print(json.dumps(line), flush=True)
@@ -115,6 +119,8 @@ def main():
     ap.add_argument("--whole-steps", type=int, default=0,
                     help="time N WHOLE 12-hour steps instead: column physics on tiles (greb_b200_tile_phase) + the two "
                          "circulations on the persistent path; checks N GPUs == 1 GPU bit for bit first")
+    ap.add_argument("--no-prefetch", action="store_true",
+                    help="--whole-steps: prepare every step's forcing on the critical path (the first version)")
     args = ap.parse_args()
 
     import torch

@@ -3,6 +3,7 @@
 //
 //   greb [namelist ...]            one member per namelist, all of them stepped as ONE ensemble on the GPU
 //   greb --check [namelist ...]    parse only: print what would run (one JSON line per namelist), no GPU
+//   greb --original [namelist_original]   the greb-original driver (control run + scenario, `log_exp` experiments)
 //   options: --input DIR (default "input"), --device N, --arith exact|fast
 //
 // Like the reference: with no argument the file `namelist` is read (f:1030-1037); the four groups
@@ -14,6 +15,7 @@
 // The Python twin of this file (the one the tests drive) is greb_b200/host.py; both produce the same bytes.
 //
 // Exit codes: 0 ok, 2 usage / namelist / input error, 3 the library reported an error (message on stderr).
+#include <algorithm>
 #include <cctype>
 #include <cerrno>
 #include <cmath>
@@ -454,21 +456,177 @@ void print_check(const std::string& file, const RunConfig& c) {
     }                                                                                               \
   } while (0)
 
+// ---- greb-original (reference src/greb.original.model.f90:138-233, shell :16-60) ---------------------------
+// log_exp -> process switches (include/greb_b200.h) and the input / CO2 changes of orig:162-166, 178-179, 225,
+// 939-951.  Same table as greb_b200/host.py (ORIGINAL_EXPERIMENTS, original_experiment).
+unsigned original_switches(int log_exp) {
+  const unsigned nocrcl = GREB_SW_NO_HEAT_CIRCULATION | GREB_SW_NO_VAPOR_CIRCULATION;
+  const unsigned ebm = GREB_SW_NO_ICE_ALBEDO | GREB_SW_NO_HYDRO | GREB_SW_NO_DEEP_OCEAN | nocrcl;
+  switch (log_exp) {
+    case 1: case 2: case 3: case 4: return ebm;
+    case 5: return GREB_SW_NO_ICE_ALBEDO | GREB_SW_NO_HYDRO | GREB_SW_NO_DEEP_OCEAN;
+    case 6: return GREB_SW_NO_HYDRO | GREB_SW_NO_DEEP_OCEAN;
+    case 7: return GREB_SW_NO_VAPOR_CIRCULATION | GREB_SW_NO_DEEP_OCEAN;
+    case 8: return GREB_SW_VAPOR_DIFFUSION_ONLY | GREB_SW_NO_DEEP_OCEAN;
+    case 9: return GREB_SW_NO_DEEP_OCEAN;
+    case 10: case 12: return 0;
+    case 11: return GREB_SW_LINEAR_VAPOR_EMISSIVITY | GREB_SW_NO_DEEP_OCEAN;
+    case 13: return GREB_SW_NO_HYDRO;
+    case 14: return GREB_SW_SST_PLUS_1K | GREB_SW_NO_DEEP_OCEAN;
+    case 15: return GREB_SW_SST_PLUS_1K | GREB_SW_NO_DEEP_OCEAN | GREB_SW_NO_HYDRO;
+    case 16: return GREB_SW_SST_PLUS_1K | GREB_SW_NO_DEEP_OCEAN | GREB_SW_NO_VAPOR_CIRCULATION;
+    default: throw NamelistError("log_exp = " + std::to_string(log_exp) + ": not an experiment of greb.original.model.f90 (1..16)");
+  }
+}
+
+float a1b_co2(float year) {                       // orig:945-951, fp32 like the reference (`year` is a real)
+  float co2 = 680.0f;
+  if (year <= 2000.0f) co2 = 310.0f + (60.0f / 50.0f) * (year - 1950.0f);
+  if (2000.0f < year && year <= 2050.0f) co2 = 370.0f + (150.0f / 50.0f) * (year - 2000.0f);
+  if (2050.0f < year && year <= 2100.0f) co2 = 520.0f + (180.0f / 50.0f) * (year - 2050.0f);
+  return co2;
+}
+
+struct OriginalConfig {
+  int time_flux = 0, time_ctrl = 0, time_scnr = 0, log_exp = 0;   // orig:60: log_exp defaults to 0
+};
+
+OriginalConfig original_from_namelist(const std::string& text) {
+  auto g = parse_namelist(text);
+  OriginalConfig c;
+  auto geti = [](Group& grp, const char* k, int dflt) {
+    auto it = grp.find(k);
+    if (it == grp.end() || it->second.empty() || it->second[0].kind == Value::NONE) return dflt;
+    return (int)it->second[0].number(k);
+  };
+  c.time_flux = geti(g["numerics"], "time_flux", 0);
+  c.time_ctrl = geti(g["numerics"], "time_ctrl", 0);
+  c.time_scnr = geti(g["numerics"], "time_scnr", 0);
+  c.log_exp = geti(g["physics"], "log_exp", 0);
+  return c;
+}
+
+// `output/control`: 730 records of TF_correct (orig:204-206), the control run's monthly means written over them
+// from record 1 (orig:209-215, unit 21)
+void write_control(const std::string& path, const std::vector<float>& tf, const std::vector<float>& ctrl) {
+  std::vector<float> out(std::max(tf.size(), ctrl.size()), 0.0f);
+  std::copy(tf.begin(), tf.end(), out.begin());
+  std::copy(ctrl.begin(), ctrl.end(), out.begin());
+  make_dirs(path);
+  FILE* f = std::fopen(path.c_str(), "wb");
+  if (!f) throw std::runtime_error(path + ": cannot open output file");
+  const size_t put = std::fwrite(out.data(), sizeof(float), out.size(), f);
+  std::fclose(f);
+  if (put != out.size()) throw std::runtime_error(path + ": short write");
+}
+
 }  // namespace
+
+static int run_original(const std::string& file, const std::string& input_dir, int device, const std::string& arith,
+                        bool check) {
+  OriginalConfig c;
+  unsigned sw = 0;
+  try {
+    c = original_from_namelist(read_text(file));
+    sw = original_switches(c.log_exp);
+  } catch (const std::exception& e) {
+    std::fprintf(stderr, "greb: %s\n", e.what());
+    return 2;
+  }
+  const bool a1b = c.log_exp == 12 || c.log_exp == 13;
+  const float co2_ctrl = a1b ? 298.0f : 340.0f;                        // orig:178-179
+  const int tc = std::max(c.time_ctrl, 0), ts = std::max(c.time_scnr, 0);
+  std::vector<float> co2((size_t)tc, co2_ctrl);
+  for (int y = 0; y < ts; ++y)                                         // the scenario starts in 1940, orig:219
+    co2.push_back(a1b ? a1b_co2((float)(1940 + y)) : (c.log_exp >= 14 ? co2_ctrl : 680.0f));   // orig:225, 943
+  if (check) {
+    std::printf("{\"namelist\": \"%s\", \"time_flux\": %d, \"time_ctrl\": %d, \"time_scnr\": %d, \"log_exp\": %d, "
+                "\"switches\": %u, \"co2_ctrl\": %.9g, \"co2\": [",
+                json_escape(file).c_str(), c.time_flux, c.time_ctrl, c.time_scnr, c.log_exp, sw, (double)co2_ctrl);
+    for (size_t i = 0; i < co2.size(); ++i) std::printf("%s%.9g", i ? ", " : "", (double)co2[i]);
+    std::printf("]}\n");
+    return 0;
+  }
+  const size_t NC = GREB_NCELL, NT = GREB_NSTEP_YR;
+  std::vector<float> z_topo, glacier, sw_solar, tclim, qclim, swet, uclim, vclim, mld, cld;
+  try {
+    z_topo = read_field(input_dir, "topography", NC);
+    glacier = read_field(input_dir, "glacier.masks", NC);
+    sw_solar = read_field(input_dir, "solar.radiation", NT * GREB_YDIM);
+    tclim = read_field(input_dir, "tsurf", NT * NC);
+    qclim = read_field(input_dir, "vapor", NT * NC);
+    swet = read_field(input_dir, "soil.moisture", NT * NC);
+    uclim = read_field(input_dir, "zonal.wind", NT * NC);
+    vclim = read_field(input_dir, "meridional.wind", NT * NC);
+    mld = read_field(input_dir, "ocean.mld", NT * NC);
+    cld = read_field(input_dir, "cloud.cover", NT * NC);
+  } catch (const std::exception& e) {
+    std::fprintf(stderr, "greb: %s\n", e.what());
+    return 2;
+  }
+  greb_physics_par p;
+  greb_b200_physics_original(&p);
+  if (c.log_exp == 1)                                                  // orig:162 constant topography
+    for (auto& z : z_topo) z = z > 1.0f ? 1.0f : z;
+  if (c.log_exp <= 2) std::fill(cld.begin(), cld.end(), 0.7f);         // orig:163 constant cloud cover
+  if (c.log_exp <= 3) std::fill(qclim.begin(), qclim.end(), 0.0052f);  // orig:164 constant water vapour
+  if (c.log_exp <= 9 || c.log_exp == 11) std::fill(mld.begin(), mld.end(), p.d_ocean);   // orig:165-166
+  p.co2_flux = co2_ctrl;
+  std::printf(" %% time flux/control/scenario:  %d %d %d\n", c.time_flux, c.time_ctrl, c.time_scnr);   // shell:59
+
+  greb_b200_t h = nullptr;
+  LIB(greb_b200_create(&h, 1, device));
+  LIB(greb_b200_set_arithmetic(h, arith == "fast" ? GREB_ARITH_FAST : GREB_ARITH_EXACT));
+  LIB(greb_b200_set_forcing(h, z_topo.data(), glacier.data(), sw_solar.data(), tclim.data(), qclim.data(), swet.data(),
+                            uclim.data(), vclim.data(), mld.data(), cld.data()));
+  const float one = 680.0f;
+  LIB(greb_b200_set_member(h, 0, &p, co2.empty() ? &one : co2.data(), co2.empty() ? 1 : (int)co2.size(), 1970));
+  LIB(greb_b200_set_switches(h, 0, sw & ~(unsigned)GREB_SW_SST_PLUS_1K));   // orig:226 applies to the scenario only
+  LIB(greb_b200_init(h));
+  LIB(greb_b200_spinup(h, c.time_flux));                               // orig:201
+  std::vector<float> tf(NT * NC);
+  LIB(greb_b200_get_fluxcorr(h, 0, 0, tf.data()));                     // orig:204-206
+  std::vector<float> ini[4];
+  for (int k = 0; k < 4; ++k) {
+    ini[k].resize(NC);
+    LIB(greb_b200_get_state(h, 0, k, ini[k].data()));
+  }
+  LIB(greb_b200_reset_scenario(h));
+  const size_t year_floats = (size_t)12 * GREB_NVAR_OUT * NC;
+  std::vector<float> ctrl((size_t)tc * year_floats), scen((size_t)ts * year_floats), gmc((size_t)tc), gms((size_t)ts);
+  LIB(greb_b200_run(h, tc, ctrl.data(), nullptr, 1, gmc.data(), nullptr));        // orig:209-215
+  for (int k = 0; k < 4; ++k) LIB(greb_b200_set_state(h, 0, k, ini[k].data()));   // orig:219
+  LIB(greb_b200_set_switches(h, 0, sw));
+  LIB(greb_b200_run(h, ts, scen.data(), nullptr, 1, gms.data(), nullptr));        // orig:220-231
+  for (int y = 0; y < tc; ++y) std::printf("   %12.6f   %12.6f   %12.8f\n", (double)(1970 + y), (double)co2_ctrl, (double)gmc[(size_t)y]);
+  for (int y = 0; y < ts; ++y)
+    std::printf("   %12.6f   %12.6f   %12.8f\n", (double)(1940 + y), (double)co2[(size_t)(tc + y)], (double)gms[(size_t)y]);
+  int rc = 0;
+  try {
+    write_control("output/control", tf, ctrl);
+    if (ts > 0) write_output("output/scenario", scen.data(), scen.size());
+  } catch (const std::exception& e) {
+    std::fprintf(stderr, "greb: %s\n", e.what());
+    rc = 2;
+  }
+  greb_b200_destroy(h);
+  return rc;
+}
 
 int main(int argc, char** argv) {
   std::vector<std::string> files;
   std::string input_dir = "input", arith = "exact";
   int device = 0;
-  bool check = false;
+  bool check = false, original = false;
   for (int i = 1; i < argc; ++i) {
     const std::string a = argv[i];
     if (a == "--check") check = true;
+    else if (a == "--original") original = true;
     else if (a == "--input" && i + 1 < argc) input_dir = argv[++i];
     else if (a == "--device" && i + 1 < argc) device = std::atoi(argv[++i]);
     else if (a == "--arith" && i + 1 < argc) arith = argv[++i];
     else if (a == "-h" || a == "--help" || (a.size() > 1 && a[0] == '-' && a[1] == '-')) {
-      std::fprintf(stderr, "usage: greb [--check] [--input DIR] [--device N] [--arith exact|fast] [namelist ...]\n");
+      std::fprintf(stderr, "usage: greb [--check] [--original] [--input DIR] [--device N] [--arith exact|fast] [namelist ...]\n");
       return a == "-h" || a == "--help" ? 0 : 2;
     } else files.push_back(a);
   }
@@ -476,6 +634,7 @@ int main(int argc, char** argv) {
     std::fprintf(stderr, "greb: --arith must be exact or fast\n");
     return 2;
   }
+  if (original) return run_original(files.empty() ? "namelist_original" : files[0], input_dir, device, arith, check);
   if (files.empty()) files.push_back("namelist");                       // f:1031-1032
   std::vector<RunConfig> cfg;
   try {

@@ -141,3 +141,50 @@ def test_compiled_host_writes_the_same_bytes_as_the_python_host(binary, tmp_path
     lines = [ln for ln in r.stdout.splitlines() if not ln.lstrip().startswith("%")]
     want = [res[m]["lines"][y] for y in range(2) for m in range(2)]       # year-major, member-minor
     assert lines == want
+
+
+# ---- greb-original mode (src/greb.original.model.f90 + shell) ----------------------------------------------
+def _orig_namelist(tf, tc, ts, log_exp):
+    return f"&NUMERICS\n time_flux = {tf}\n time_ctrl = {tc}\n time_scnr = {ts}\n/\n&PHYSICS\n log_exp = {log_exp}\n/\n"
+
+
+@pytest.mark.parametrize("log_exp", list(range(1, 17)))
+def test_original_mode_plans_the_same_experiment_as_the_python_host(binary, tmp_path, forcing, log_exp):
+    path = tmp_path / "namelist_original"
+    path.write_text(_orig_namelist(1, 2, 4, log_exp))
+    r = subprocess.run([binary, "--original", "--check", str(path)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr
+    got = json.loads(r.stdout)
+    ex = host.original_experiment(log_exp, forcing, 4)
+    assert (got["time_flux"], got["time_ctrl"], got["time_scnr"], got["log_exp"]) == (1, 2, 4, log_exp)
+    assert got["switches"] == ex["switches"]
+    assert np.float32(got["co2_ctrl"]) == np.float32(ex["co2_ctrl"])
+    want = np.concatenate([np.full(2, ex["co2_ctrl"], dtype=np.float32), ex["co2_scenario"]])
+    assert np.array_equal(np.asarray(got["co2"], dtype=np.float32), want)
+
+
+def test_original_mode_rejects_an_unknown_experiment(binary, tmp_path):
+    path = tmp_path / "namelist_original"
+    path.write_text(_orig_namelist(1, 1, 1, 17))
+    r = subprocess.run([binary, "--original", "--check", str(path)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 2 and "log_exp" in r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("log_exp", [10, 5, 13])
+def test_original_mode_writes_the_same_control_and_scenario_files(binary, tmp_path, forcing, log_exp):
+    """full model, an experiment with modified inputs (mld = d_ocean) and the A1B pathway without hydrology"""
+    forcing.write(str(tmp_path / "input"))
+    path = tmp_path / "namelist_original"
+    path.write_text(_orig_namelist(1, 1, 2, log_exp))
+    py_dir, c_dir = tmp_path / "py", tmp_path / "c"
+    py_dir.mkdir()
+    c_dir.mkdir()
+    host.run_original_namelist(str(path), input_dir=str(tmp_path / "input"), workdir=str(py_dir))
+    r = subprocess.run([binary, "--original", "--input", str(tmp_path / "input"), str(path)], cwd=c_dir,
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr
+    for name, size in (("control", 730 * 96 * 48 * 4), ("scenario", 2 * 12 * 5 * 96 * 48 * 4)):
+        a = (py_dir / "output" / name).read_bytes()
+        b = (c_dir / "output" / name).read_bytes()
+        assert len(a) == size and a == b, name

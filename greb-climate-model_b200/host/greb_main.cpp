@@ -4,7 +4,8 @@
 //   greb [namelist ...]            one member per namelist, all of them stepped as ONE ensemble on the GPU
 //   greb --check [namelist ...]    parse only: print what would run (one JSON line per namelist), no GPU
 //   greb --original [namelist_original]   the greb-original driver (control run + scenario, `log_exp` experiments)
-//   options: --input DIR (default "input"), --device N, --arith exact|fast
+//   options: --input DIR (default "input"), --device N, --gpus G (members in contiguous blocks over devices
+//            N..N+G-1, one handle and one host thread per GPU), --arith exact|fast
 //
 // Like the reference: with no argument the file `namelist` is read (f:1030-1037); the four groups
 // physics_par, numerics_par, diagnostics_par, co2_par set the member's parameters (f:1040-1048); co2_ppm is
@@ -27,6 +28,7 @@
 #include <sstream>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <sys/stat.h>
@@ -613,10 +615,66 @@ static int run_original(const std::string& file, const std::string& input_dir, i
   return rc;
 }
 
+struct Inputs {
+  const float *z_topo, *glacier, *sw_solar, *tclim, *qclim, *swet, *uclim, *vclim, *mld, *cld;
+};
+
+// one handle = one GPU: spin-up + scenario of `n` members, their output files, their console lines
+static int run_block(const RunConfig* cfg, int n, int device, const std::string& arith, const Inputs& in,
+                     std::vector<std::string>* lines) {
+  const int N = n, tf = cfg[0].time_flux, ts = cfg[0].time_scnr;
+  const size_t NC = GREB_NCELL;
+  greb_b200_t h = nullptr;
+  LIB(greb_b200_create(&h, N, device));
+  LIB(greb_b200_set_arithmetic(h, arith == "fast" ? GREB_ARITH_FAST : GREB_ARITH_EXACT));
+  LIB(greb_b200_set_forcing(h, in.z_topo, in.glacier, in.sw_solar, in.tclim, in.qclim, in.swet, in.uclim, in.vclim,
+                            in.mld, in.cld));
+  const float co2_default = 680.0f;
+  for (int m = 0; m < N; ++m)
+    LIB(greb_b200_set_member(h, m, &cfg[m].p, ts > 0 ? cfg[m].co2_ppm.data() : &co2_default, ts > 0 ? ts : 1,
+                             cfg[m].year0));
+  LIB(greb_b200_init(h));
+  LIB(greb_b200_spinup(h, tf));                                         // f:221
+  LIB(greb_b200_reset_scenario(h));                                     // f:226-227
+  const size_t year_floats = (size_t)12 * GREB_NVAR_OUT * NC;
+  std::vector<std::vector<float>> monthly((size_t)N, std::vector<float>((size_t)(ts > 0 ? ts : 0) * year_floats));
+  std::vector<float> year((size_t)N * year_floats), gm((size_t)N);
+  static const double days[12] = {31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31};
+  for (int y = 0; y < ts; ++y) {                                        // one simulated year per launch
+    LIB(greb_b200_run(h, 1, year.data(), nullptr, N, gm.data(), nullptr));
+    for (int m = 0; m < N; ++m) {
+      const float* rec = year.data() + (size_t)m * year_floats;
+      std::memcpy(monthly[(size_t)m].data() + (size_t)y * year_floats, rec, year_floats * sizeof(float));
+      // f:954 prints tsmn(ipx,ipy)-273.15, the annual mean of Tsurf at the diagnostic point; the ABI returns
+      // monthly means, so the point value is their day-weighted mean
+      double s = 0, w = 0;
+      for (int mo = 0; mo < 12; ++mo) {
+        s += (double)rec[((size_t)mo * GREB_NVAR_OUT + 0) * NC + (size_t)(cfg[m].ipy - 1) * GREB_XDIM + (cfg[m].ipx - 1)] * days[mo];
+        w += days[mo];
+      }
+      const float point = (float)(s / w - 273.15);
+      char buf[160];
+      std::snprintf(buf, sizeof buf, "   %12.6f   %12.6f   %12.8f   %12.8f\n", (double)(cfg[m].year0 + y),
+                    (double)cfg[m].co2_ppm[(size_t)y], (double)gm[(size_t)m], (double)point);
+      lines[m].push_back(buf);
+    }
+  }
+  int rc = 0;
+  try {
+    for (int m = 0; m < N; ++m)
+      if (ts > 0) write_output(cfg[m].output_file_full(), monthly[(size_t)m].data(), monthly[(size_t)m].size());
+  } catch (const std::exception& e) {
+    std::fprintf(stderr, "greb: %s\n", e.what());
+    rc = 2;
+  }
+  greb_b200_destroy(h);
+  return rc;
+}
+
 int main(int argc, char** argv) {
   std::vector<std::string> files;
   std::string input_dir = "input", arith = "exact";
-  int device = 0;
+  int device = 0, gpus = 1;
   bool check = false, original = false;
   for (int i = 1; i < argc; ++i) {
     const std::string a = argv[i];
@@ -625,8 +683,9 @@ int main(int argc, char** argv) {
     else if (a == "--input" && i + 1 < argc) input_dir = argv[++i];
     else if (a == "--device" && i + 1 < argc) device = std::atoi(argv[++i]);
     else if (a == "--arith" && i + 1 < argc) arith = argv[++i];
+    else if (a == "--gpus" && i + 1 < argc) gpus = std::atoi(argv[++i]);
     else if (a == "-h" || a == "--help" || (a.size() > 1 && a[0] == '-' && a[1] == '-')) {
-      std::fprintf(stderr, "usage: greb [--check] [--original] [--input DIR] [--device N] [--arith exact|fast] [namelist ...]\n");
+      std::fprintf(stderr, "usage: greb [--check] [--original] [--input DIR] [--device N] [--gpus G] [--arith exact|fast] [namelist ...]\n");
       return a == "-h" || a == "--help" ? 0 : 2;
     } else files.push_back(a);
   }
@@ -673,47 +732,25 @@ int main(int argc, char** argv) {
   for (const auto& c : cfg)
     std::printf(" %% diagonstic point lat/lon:  %g %g\n", 3.75 * c.ipy - 90, 3.75 * c.ipx);   // f:1070
 
-  greb_b200_t h = nullptr;
-  LIB(greb_b200_create(&h, N, device));
-  LIB(greb_b200_set_arithmetic(h, arith == "fast" ? GREB_ARITH_FAST : GREB_ARITH_EXACT));
-  LIB(greb_b200_set_forcing(h, z_topo.data(), glacier.data(), sw_solar.data(), tclim.data(), qclim.data(), swet.data(),
-                            uclim.data(), vclim.data(), mld.data(), cld.data()));
-  const float co2_default = 680.0f;
-  for (int m = 0; m < N; ++m)
-    LIB(greb_b200_set_member(h, m, &cfg[m].p, ts > 0 ? cfg[m].co2_ppm.data() : &co2_default, ts > 0 ? ts : 1,
-                             cfg[m].year0));
-  LIB(greb_b200_init(h));
-  LIB(greb_b200_spinup(h, tf));                                         // f:221
-  LIB(greb_b200_reset_scenario(h));                                     // f:226-227
-  const size_t year_floats = (size_t)12 * GREB_NVAR_OUT * NC;
-  std::vector<std::vector<float>> monthly((size_t)N, std::vector<float>((size_t)(ts > 0 ? ts : 0) * year_floats));
-  std::vector<float> year((size_t)N * year_floats), gm((size_t)N);
-  static const double days[12] = {31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31};
-  for (int y = 0; y < ts; ++y) {                                        // one simulated year per launch
-    LIB(greb_b200_run(h, 1, year.data(), nullptr, N, gm.data(), nullptr));
-    for (int m = 0; m < N; ++m) {
-      const float* rec = year.data() + (size_t)m * year_floats;
-      std::memcpy(monthly[(size_t)m].data() + (size_t)y * year_floats, rec, year_floats * sizeof(float));
-      // f:954 prints tsmn(ipx,ipy)-273.15, the annual mean of Tsurf at the diagnostic point; the ABI returns
-      // monthly means, so the point value is their day-weighted mean
-      double s = 0, w = 0;
-      for (int mo = 0; mo < 12; ++mo) {
-        s += (double)rec[((size_t)mo * GREB_NVAR_OUT + 0) * NC + (size_t)(cfg[m].ipy - 1) * GREB_XDIM + (cfg[m].ipx - 1)] * days[mo];
-        w += days[mo];
-      }
-      const float point = (float)(s / w - 273.15);
-      std::printf("   %12.6f   %12.6f   %12.8f   %12.8f\n", (double)(cfg[m].year0 + y), (double)cfg[m].co2_ppm[(size_t)y],
-                  (double)gm[(size_t)m], (double)point);
-    }
+  // members in contiguous blocks over the GPUs (heights differ by at most one), one handle and one host thread
+  // per GPU; members never interact, so there is no exchange between the blocks
+  const int G = std::max(1, std::min(gpus, N));
+  const Inputs in{z_topo.data(), glacier.data(), sw_solar.data(), tclim.data(), qclim.data(), swet.data(),
+                  uclim.data(), vclim.data(), mld.data(), cld.data()};
+  std::vector<std::vector<std::string>> lines((size_t)N);
+  std::vector<int> rcs((size_t)G, 0);
+  std::vector<std::thread> threads;
+  for (int g = 0; g < G; ++g) {
+    const int m0 = (int)((long)N * g / G), m1 = (int)((long)N * (g + 1) / G);
+    threads.emplace_back([&, g, m0, m1] {
+      rcs[(size_t)g] = run_block(cfg.data() + m0, m1 - m0, device + g, arith, in, lines.data() + m0);
+    });
   }
-  int rc = 0;
-  try {
+  for (auto& t : threads) t.join();
+  for (int y = 0; y < ts; ++y)                                          // the console lines, year by year
     for (int m = 0; m < N; ++m)
-      if (ts > 0) write_output(cfg[m].output_file_full(), monthly[(size_t)m].data(), monthly[(size_t)m].size());
-  } catch (const std::exception& e) {
-    std::fprintf(stderr, "greb: %s\n", e.what());
-    rc = 2;
-  }
-  greb_b200_destroy(h);
-  return rc;
+      if ((size_t)y < lines[(size_t)m].size()) std::fputs(lines[(size_t)m][(size_t)y].c_str(), stdout);
+  for (int rc : rcs)
+    if (rc != 0) return rc;
+  return 0;
 }

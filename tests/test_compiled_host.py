@@ -188,3 +188,29 @@ def test_original_mode_writes_the_same_control_and_scenario_files(binary, tmp_pa
         a = (py_dir / "output" / name).read_bytes()
         b = (c_dir / "output" / name).read_bytes()
         assert len(a) == size and a == b, name
+
+
+@pytest.mark.gpu
+def test_compiled_host_shards_members_over_gpus(binary, tmp_path, forcing):
+    """--gpus 2: three members in blocks over two GPUs (one handle and one host thread each) write the same files
+    and print the same lines as one GPU — members never interact, there is nothing to exchange"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    forcing.write(str(tmp_path / "input"))
+    nml = []
+    for ens_id, co2, kappa in (("a", 680.0, 8e5), ("b", 400.0, 9.4e5), ("c", 900.0, 7e5)):
+        path = tmp_path / f"namelist_{ens_id}"
+        path.write_text(f"&PHYSICS_PAR\n kappa = {kappa}\n/\n&NUMERICS_PAR\n time_flux = 1\n time_scnr = 2\n/\n"
+                        f"&DIAGNOSTICS_PAR\n ens_id = \"{ens_id}\"\n/\n&CO2_PAR\n co2_ppm = {co2}\n/\n")
+        nml.append(str(path))
+    outs = {}
+    for g in (1, 2):
+        d = tmp_path / f"g{g}"
+        d.mkdir()
+        r = subprocess.run([binary, "--gpus", str(g), "--input", str(tmp_path / "input")] + nml, cwd=d,
+                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        assert r.returncode == 0, r.stderr
+        outs[g] = (r.stdout, [(d / "output" / f"scenario_{e}").read_bytes() for e in "abc"])
+    assert outs[1][0] == outs[2][0]
+    assert outs[1][1] == outs[2][1] and all(len(b) == 2 * 12 * 5 * 96 * 48 * 4 for b in outs[2][1])

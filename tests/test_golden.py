@@ -10,6 +10,7 @@ a GPU: they pin the hand-written C oracle (oracle/greb_oracle.c) bit for bit on
   * config 1 (reference `namelist`): 3-yr flux correction + 50 yr at 680 ppm — every one of the 3,000
     output records and the yearly console line (f:954);
   * a perturbed-physics member with a CO2 ramp (co2_ppm padding rule f:1053-1061);
+  * the two low-CO2 members of the perturbed ensemble with a bistable sea-ice edge (3 + 12 years, every record);
   * config 2 (greb-original, log_exp=10): spin-up and control run at 340 ppm, `output/control`
     (TF_correct records overwritten by the control run's monthly means), 50-yr scenario.
 
@@ -39,7 +40,7 @@ def first_diff(a, b):
 
 
 def test_fixtures_match_the_synthetic_forcing(forcing):
-    for name in ("ref_kernels.npz", "ref_config1.npz", "ref_perturbed.npz", "ref_config2.npz"):
+    for name in ("ref_kernels.npz", "ref_config1.npz", "ref_perturbed.npz", "ref_config2.npz", "ref_members.npz"):
         assert str(load(name)["forcing_digest"]) == forcing.digest(), name
 
 
@@ -141,6 +142,35 @@ def test_perturbed_member_with_co2_ramp(oracle_mod, forcing):
     scen = con[con[:, 0] >= 2000]
     assert np.array_equal(scen[:, 1], co2.astype(np.float64))
     assert np.array_equal(scen[:, 2].astype(np.float32), gm)
+
+
+def test_bistable_low_co2_members_bit_exact(oracle_mod, forcing):
+    """Members 22 and 2989 of the perturbed ensemble (CO2 < 300 ppm, all six physics parameters perturbed): the two
+    on which the GPU's fast arithmetic leaves the 0.01 K gate while its exact mode equals the oracle bit for bit over
+    3 + 50 years (tests/test_gpu_long_parity.py).  Here the oracle itself is pinned on them by the translated
+    reference: every record of 3 + 12 years and the console values (tests/golden/make_golden_members.py)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from greb_b200 import campaign
+    g = load("ref_members.npz")
+    assert str(g["forcing_digest"]) == forcing.digest()
+    spinup, years = int(g["spinup"]), int(g["years"])
+
+    def run(m):
+        p, co2 = campaign.perturbed_member(int(m))
+        assert np.float32(co2) == np.float32(g[f"m{m}_co2"])
+        o = oracle_mod.Oracle(forcing, **{k: getattr(p, k) for k in ("kappa", "ct_sens", "ce", "co_turb", "a_cloud", "da_ice")})
+        o.spinup(spinup)
+        out, gm = o.run(years, co2_ppm=co2)
+        return out.reshape(-1, 48, 96), gm
+
+    with ThreadPoolExecutor(2) as pool:                      # the oracle releases the GIL inside its C loops
+        res = list(pool.map(run, g["members"]))
+    for m, (out, gm) in zip(g["members"], res):
+        assert first_diff(digests(out), g[f"m{m}_digests"]) is None, int(m)
+        assert np.array_equal(out[((10 - 1) * 12 + 11) * 5:((10 - 1) * 12 + 11) * 5 + 5], g[f"m{m}_dec_year10"])
+        con = g[f"m{m}_console"]
+        scen = con[con[:, 0] >= 1940]
+        assert scen.shape[0] == years and np.array_equal(scen[:, 2].astype(np.float32), gm), int(m)
 
 
 def test_config2_original_model_control_and_scenario(long_runs):

@@ -130,3 +130,34 @@ def test_run_namelists_batch_writes_reference_format(forcing, tmp_path, oracle_m
                 check_records(got[y, m], want[y, m], f"{ens_id} y{y} m{m}")
         assert np.abs(r["gmean"] - gm).max() <= TOL_GM
         assert len(r["lines"]) == 2
+
+
+def test_bistable_members_exact_mode_equals_the_reference_record_for_record(forcing):
+    """The two low-CO2 members of the perturbed ensemble on which the fast arithmetic drifts (members 22 and
+    2989, tests/test_gpu_long_parity.py): the default (exact) arithmetic reproduces what the translated reference
+    wrote for them — every one of the 720 records of 3 + 12 years — digest for digest, no oracle in the loop."""
+    import hashlib
+    from greb_b200 import campaign
+    g = load("ref_members.npz")
+    assert str(g["forcing_digest"]) == forcing.digest()
+    members = [int(m) for m in g["members"]]
+    spinup, years = int(g["spinup"]), int(g["years"])
+    ens = greb_b200.Ensemble(len(members))
+    ens.set_arithmetic("exact")
+    ens.set_forcing(forcing)
+    for i, m in enumerate(members):
+        p, co2 = campaign.perturbed_member(m)
+        ens.set_member(i, p, np.full(years, co2, dtype=np.float32))
+    ens.init()
+    ens.spinup(spinup)
+    ens.reset_scenario()
+    out, gm, _ = ens.run(years)
+    ens.close()
+    for i, m in enumerate(members):
+        recs = np.where(out[i] == 0, np.float32(0), out[i]).reshape(-1, 48, 96)      # signs of zeros aside
+        dig = np.array([hashlib.sha1(np.ascontiguousarray(r, dtype="<f4").tobytes()).hexdigest()[:16] for r in recs])
+        bad = np.nonzero(dig != g[f"m{m}_digests"])[0]
+        assert bad.size == 0, (m, int(bad[0]))
+        con = g[f"m{m}_console"]
+        scen = con[con[:, 0] >= 1940]
+        assert np.array_equal(scen[:, 2].astype(np.float32), gm[i]), m

@@ -11,6 +11,7 @@ import greb_b200
 from greb_b200 import lib as gl
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG_DIR = os.path.join(ROOT, "greb-climate-model_b200")
 
 
 def test_header_symbols_are_exported():
@@ -69,3 +70,47 @@ def test_product_sources_do_not_reference_the_oracle():
                     if re.search(r"greb_oracle|from oracle|import oracle|oracle/", txt):
                         bad.append(os.path.join(dp, fn))
     assert not bad, bad
+
+
+def test_headers_are_plain_c99_and_link_from_c(tmp_path):
+    """The boundary is a C ABI: both headers compile as pedantic C99, and a C program linked against the library
+    calls the host-side entries (defaults, CO2 padding) and gets an error code — not a crash — from
+    greb_b200_create when there is no GPU."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "abi.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include "greb_b200.h"
+#include "greb_grid.h"
+int main(void) {
+  greb_physics_par p;
+  float co2[4];
+  const float given[2] = {-1.0f, 400.0f};
+  greb_b200_t h = 0;
+  int rc;
+  greb_b200_physics_defaults(&p);
+  greb_b200_pad_co2(given, 2, co2, 4);
+  rc = greb_b200_create(&h, 1, 0);
+  printf("%g %g %g %g %g %d %s\n", (double)p.kappa, (double)co2[0], (double)co2[1], (double)co2[2], (double)co2[3], rc,
+         rc == GREB_OK ? "ok" : greb_b200_last_error(0));
+  if (h) greb_b200_destroy(h);
+  return 0;
+}
+''')
+    exe = tmp_path / "abi"
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                        str(src), "-L", PKG_DIR, "-lgreb_b200", f"-Wl,-rpath,{PKG_DIR}", "-o", str(exe)],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    r = subprocess.run([str(exe)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    f = r.stdout.split(None, 6)
+    assert [float(x) for x in f[:5]] == [8e5, 680.0, 400.0, 400.0, 400.0]
+    import torch
+    if torch.cuda.is_available():
+        assert int(f[5]) == 0
+    else:
+        assert int(f[5]) == -2 and len(f[6].strip()) > 0          # GREB_E_NO_DEVICE with a message

@@ -606,7 +606,7 @@ static int run_original(const std::string& file, const std::string& input_dir, i
   int rc = 0;
   try {
     write_control("output/control", tf, ctrl);
-    if (ts > 0) write_output("output/scenario", scen.data(), scen.size());
+    write_output("output/scenario", scen.data(), scen.size());
   } catch (const std::exception& e) {
     std::fprintf(stderr, "greb: %s\n", e.what());
     rc = 2;
@@ -662,7 +662,7 @@ static int run_block(const RunConfig* cfg, int n, int device, const std::string&
   int rc = 0;
   try {
     for (int m = 0; m < N; ++m)
-      if (ts > 0) write_output(cfg[m].output_file_full(), monthly[(size_t)m].data(), monthly[(size_t)m].size());
+      write_output(cfg[m].output_file_full(), monthly[(size_t)m].data(), monthly[(size_t)m].size());   // opened even for 0 years, f:174
   } catch (const std::exception& e) {
     std::fprintf(stderr, "greb: %s\n", e.what());
     rc = 2;
